@@ -1,0 +1,165 @@
+/* b200wgcna -- C ABI of the B200-native (sm_100a) network-construction hot path of PyWGCNA.
+ *
+ * This header is the drop-in boundary.  The reference (mortazavilab/PyWGCNA 2.2.0) has no
+ * FFI: its "operator interface" for this path is three static methods that findModules looks
+ * up on the class by name (PyWGCNA/wgcna.py:278, :310, :320).  Each entry point below names
+ * the reference lines whose arithmetic it replaces; pywgcna_b200/wgcna.py binds them with
+ * ctypes behind the reference's own Python signatures.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all matrices are IEEE float64, C order (row-major);
+ *   - every function returns 0 on success or a negative B200W_E_* code; the message of the
+ *     last failure on the calling thread is b200w_last_error();
+ *   - "host" entry points take HOST pointers and do H2D -> kernels -> D2H on `device`;
+ *     "dev" entry points take DEVICE pointers valid on `device`, enqueue on `stream`
+ *     (a cudaStream_t passed as void*, NULL = default stream) and do not synchronise;
+ *   - there is no CPU fallback: without a usable sm_100 device every compute call fails
+ *     with B200W_E_NO_DEVICE.
+ *   - row blocks: [row0, row0 + nrows) selects the output rows one GPU owns (multi-GPU
+ *     row-block sharding); nrows == n, row0 == 0 is the whole matrix.
+ */
+#ifndef B200WGCNA_H
+#define B200WGCNA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200W_VERSION 100
+
+/* error codes */
+#define B200W_OK 0
+#define B200W_E_INVALID -1   /* bad argument (enum value, size, NULL pointer) */
+#define B200W_E_NO_DEVICE -2 /* no CUDA device / not an sm_100 part */
+#define B200W_E_CUDA -3      /* a CUDA runtime call or kernel failed */
+#define B200W_E_NOMEM -4     /* device allocation failed */
+#define B200W_E_UNSUPPORTED -5
+
+/* networkTypes / adjacencyTypes, index order of wgcna.py:53-54 */
+#define B200W_NET_UNSIGNED 0
+#define B200W_NET_SIGNED 1
+#define B200W_NET_SIGNED_HYBRID 2
+/* TOMTypes wgcna.py:55, TOMDenoms wgcna.py:56 */
+#define B200W_TOM_UNSIGNED 0
+#define B200W_TOM_SIGNED 1
+#define B200W_DENOM_MIN 0
+#define B200W_DENOM_MEAN 1
+/* what the TOM epilogue writes */
+#define B200W_OUT_TOM 0      /* TOM, diagonal 1                 (wgcna.py:1153-1156) */
+#define B200W_OUT_DISS 1     /* 1 - TOM                         (wgcna.py:323)       */
+#define B200W_OUT_DISS_R8 2  /* rint((1 - TOM) * 1e8) / 1e8     (wgcna.py:323-324)   */
+/* arithmetic of the A.A contraction */
+#define B200W_PREC_AUTO 0    /* = B200W_PREC_I8 */
+#define B200W_PREC_F64 1     /* FP64 tensor-core DMMA (mma.sync f64)                    */
+#define B200W_PREC_I8 2      /* tcgen05 kind::i8, exact int32 accumulation of fixed-point
+                                digit slices (row-scaled, 5 slices = 39 bits)            */
+
+int b200w_version(void);
+const char* b200w_last_error(void);
+/* number of visible CUDA devices with compute capability 10.x (0 if none) */
+int b200w_device_count(void);
+
+/* ------------------------------------------------------------------ host entry points */
+
+/* Connectivity of the soft-threshold sweep: replaces the block loop of
+ * WGCNA.pickSoftThreshold, wgcna.py:873-920 (np.corrcoef :882, transforms :884-889,
+ * diag<-1 :897, power chain and nansum :900-916).
+ *   X        m x n expression (rows samples, columns genes)
+ *   steps    P power STEPS: steps[j] = powers[j] - powers[j-1] for the ascending power
+ *            vector (wgcna.py:901-903)
+ *   k_out    P x n : k_out[j*n + g] = datk[g, j] of the reference (transposed layout)
+ *   bad_out  optional (may be NULL) n flags: 1 for genes whose np.corrcoef row is NaN
+ *            (a non-finite sample or zero variance) */
+int b200w_connectivity_sweep(const double* X, int64_t m, int64_t n, const double* steps, int P,
+                             int net_type, double* k_out, uint8_t* bad_out, int device);
+
+/* WGCNA.adjacency, wgcna.py:1097-1111 (corrcoef, transform, ** power).
+ *   A_out    nrows x n row block of the n x n adjacency */
+int b200w_adjacency(const double* X, int64_t m, int64_t n, int net_type, double power,
+                    int64_t row0, int64_t nrows, double* A_out, int device);
+
+/* The three reductions WGCNA.checkAdjMat needs, wgcna.py:1135-1138, in one pass over A.
+ *   stats[0] = max |A - A^T| over non-NaN pairs, stats[1] = min, stats[2] = max (NaN ignored),
+ *   stats[3] = number of NaN entries (numpy's max/min return NaN if any is present, which
+ *   makes every check of the reference pass; the host logic reproduces that). */
+int b200w_check_adjacency(const double* A, int64_t n, double* stats, int device);
+
+/* WGCNA.TOMsimilarity / TomSimilarityFromAdj, wgcna.py:1185 (NaN -> 0), :1143 (diag <- 0),
+ * :1145 (A @ A), :1146-1151 (k, min/mean denominator), :1153/:1155, :1156 (diag <- 1).
+ * The input is not modified.  out is the nrows x n row block.
+ * With check != 0 the checkAdjMat reductions run first on the device copy (stats4 as in
+ * b200w_check_adjacency, may be NULL) and the call returns, without computing,
+ *   B200W_CHECK_ASYMMETRIC  if max|A - A^T| > 1e-12                     (wgcna.py:1135)
+ *   B200W_CHECK_RANGE       if min(A) < lo or max(A) > 1, lo = -1 for the signed TOM else 0 (:1137)
+ * -- unless A holds a NaN, which makes both numpy comparisons of the reference False. */
+#define B200W_CHECK_ASYMMETRIC 1
+#define B200W_CHECK_RANGE 2
+int b200w_tom(const double* A, int64_t n, int tom_type, int tom_denom, int out_mode, int precision,
+              int64_t row0, int64_t nrows, double* out, int check, double* stats4, int device);
+
+/* Fused chain adjacency -> TOM with the adjacency kept in HBM:
+ * equivalent to b200w_adjacency followed by b200w_tom on its result.  A_out may be NULL. */
+int b200w_network(const double* X, int64_t m, int64_t n, int net_type, double power, int tom_type,
+                  int tom_denom, int out_mode, int precision, double* A_out, double* tom_out,
+                  int device);
+
+/* WGCNA.intramodularConnectivity, wgcna.py:3431-3445: diag <- 0, NaN -> 0, per-module
+ * within-module row sums.  labels[n] are module ids in [0, nmod); small[nmod] != 0 marks
+ * modules with < 3 genes (kWithin = 0, :3436).  out: kTotal[n], kWithin[n]. */
+int b200w_intramodular(const double* A, int64_t n, const int32_t* labels, int nmod,
+                       const uint8_t* small, double* k_total, double* k_within, int device);
+
+/* ---------------------------------------------------------------- device entry points */
+
+/* bytes of scratch the dev_* calls need are allocated stream-ordered internally. */
+
+/* centre and scale every gene to unit norm: Z[g, s] = (X[s, g] - mean_g) / ||X[:, g] - mean_g||,
+ * Z is n x ldk (ldk = b200w_padded_k(m), zero padded); bad[g] = 1 for genes whose
+ * correlation row is NaN in np.corrcoef (non-finite sample or zero variance). */
+int64_t b200w_padded_k(int64_t m);
+int b200w_dev_standardize(const double* dX, int64_t m, int64_t n, double* dZ, uint8_t* d_bad,
+                          int device, void* stream);
+int b200w_dev_sweep(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t n,
+                    const double* h_steps, int P, int net_type, int64_t col0, int64_t ncols,
+                    double* d_k /* P x ncols */, int device, void* stream);
+int b200w_dev_adjacency(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t n, int net_type,
+                        double power, int64_t row0, int64_t nrows, double* dA, int device,
+                        void* stream);
+int b200w_dev_check_adjacency(const double* dA, int64_t n, double* d_stats4, int device,
+                              void* stream);
+
+/* TOM on device-resident data, three steps so that a multi-GPU caller can exchange the
+ * operand between them:
+ *  (1) b200w_dev_tom_prepare: for the row block [row0,row0+nrows) of A: NaN -> 0, diag -> 0,
+ *      k = row sums, and the operand the contraction needs --
+ *        precision F64: Ac  nrows x ldn float64 (ldn = b200w_padded_n(n)), zero padded
+ *        precision I8 : Q   B200W_I8_SLICES planes of nrows x ldn int8 digits + scale[nrows]
+ *      written at row offset row0 of the FULL operand buffers (n rows), so that after an
+ *      all-gather (or with nrows == n) the buffers hold the whole operand.
+ *  (2) [multi-GPU: all-gather operand row blocks and k between ranks]
+ *  (3) b200w_dev_tom_compute: out[row block] from the full operand + k. */
+#define B200W_I8_SLICES 5
+int64_t b200w_padded_n(int64_t n);
+/* bytes of the full operand buffer for n genes at the given precision */
+int64_t b200w_tom_operand_bytes(int64_t n, int precision);
+int b200w_dev_tom_prepare(const double* dA_rows /* nrows x n */, int64_t n, int64_t row0,
+                          int64_t nrows, int precision, void* d_operand, double* d_scale /* n */,
+                          double* d_k /* n */, int device, void* stream);
+int b200w_dev_tom_compute(const double* dA_rows /* nrows x n, original */, const void* d_operand,
+                          const double* d_scale, const double* d_k, int64_t n, int64_t row0,
+                          int64_t nrows, int tom_type, int tom_denom, int out_mode, int precision,
+                          double* d_out /* nrows x n */, int device, void* stream);
+
+/* ----------------------------------------------------------------------- introspection */
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t b200w_launch_count(void);
+/* device time in ms of the most recent b200w_dev_tom_compute contraction kernel as measured by
+ * CUDA events on its stream when B200W_TIME_KERNELS=1 is set (else -1) */
+double b200w_last_kernel_ms(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200WGCNA_H */

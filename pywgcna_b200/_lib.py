@@ -1,0 +1,115 @@
+"""ctypes binding of ``libb200wgcna.so`` (C ABI declared in ``include/b200wgcna.h``).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``make -C pywgcna_b200/csrc``.  There is
+no CPU fallback: a missing library raises at first use, and every compute call raises
+``B200WError`` when no sm_100 device is usable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200wgcna.so")
+
+NET_TYPES = ["unsigned", "signed", "signed hybrid"]  # wgcna.py:53-54
+TOM_TYPES = ["unsigned", "signed"]  # wgcna.py:55
+TOM_DENOMS = ["min", "mean"]  # wgcna.py:56
+OUT_TOM, OUT_DISS, OUT_DISS_R8 = 0, 1, 2
+PREC_AUTO, PREC_F64, PREC_I8 = 0, 1, 2
+I8_SLICES = 5
+
+E_INVALID, E_NO_DEVICE, E_CUDA, E_NOMEM, E_UNSUPPORTED = -1, -2, -3, -4, -5
+
+
+class B200WError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libb200wgcna error {code}: {msg}")
+        self.code = code
+
+
+_dp = C.c_void_p  # device or host pointer, passed as integer address
+_i64 = C.c_int64
+_int = C.c_int
+_dbl = C.c_double
+
+# name -> (restype, argtypes); every symbol include/b200wgcna.h declares
+SIGNATURES = {
+    "b200w_version": (_int, []),
+    "b200w_last_error": (C.c_char_p, []),
+    "b200w_device_count": (_int, []),
+    "b200w_connectivity_sweep": (_int, [_dp, _i64, _i64, _dp, _int, _int, _dp, _dp, _int]),
+    "b200w_adjacency": (_int, [_dp, _i64, _i64, _int, _dbl, _i64, _i64, _dp, _int]),
+    "b200w_check_adjacency": (_int, [_dp, _i64, _dp, _int]),
+    "b200w_tom": (_int, [_dp, _i64, _int, _int, _int, _int, _i64, _i64, _dp, _int, _dp, _int]),
+    "b200w_network": (_int, [_dp, _i64, _i64, _int, _dbl, _int, _int, _int, _int, _dp, _dp, _int]),
+    "b200w_intramodular": (_int, [_dp, _i64, _dp, _int, _dp, _dp, _dp, _int]),
+    "b200w_padded_k": (_i64, [_i64]),
+    "b200w_dev_standardize": (_int, [_dp, _i64, _i64, _dp, _dp, _int, _dp]),
+    "b200w_dev_sweep": (_int, [_dp, _dp, _i64, _i64, _dp, _int, _int, _i64, _i64, _dp, _int, _dp]),
+    "b200w_dev_adjacency": (_int, [_dp, _dp, _i64, _i64, _int, _dbl, _i64, _i64, _dp, _int, _dp]),
+    "b200w_dev_check_adjacency": (_int, [_dp, _i64, _dp, _int, _dp]),
+    "b200w_padded_n": (_i64, [_i64]),
+    "b200w_tom_operand_bytes": (_i64, [_i64, _int]),
+    "b200w_dev_tom_prepare": (_int, [_dp, _i64, _i64, _i64, _int, _dp, _dp, _dp, _int, _dp]),
+    "b200w_dev_tom_compute": (_int, [_dp, _dp, _dp, _dp, _i64, _i64, _i64, _int, _int, _int, _int,
+                                     _dp, _int, _dp]),
+    "b200w_launch_count": (_i64, []),
+    "b200w_last_kernel_ms": (_dbl, []),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and declare every prototype."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C pywgcna_b200/csrc`.  pywgcna_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code: int):
+    if code != 0:
+        raise B200WError(code, load().b200w_last_error().decode("utf-8", "replace"))
+
+
+def hptr(a: np.ndarray) -> int:
+    """Address of a C-contiguous numpy array."""
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data
+
+
+def as_f64_matrix(x) -> np.ndarray:
+    """C-contiguous float64 2-D view/copy of ``x`` (DataFrame or array-like)."""
+    if hasattr(x, "to_numpy"):
+        x = x.to_numpy()
+    a = np.ascontiguousarray(x, dtype=np.float64)
+    if a.ndim != 2:
+        raise ValueError("expected a 2-D matrix")
+    return a
+
+
+def device_count() -> int:
+    return int(load().b200w_device_count())
+
+
+def default_device() -> int:
+    """Device the host entry points use: $B200WGCNA_DEVICE, else LOCAL_RANK (torchrun), else 0."""
+    for var in ("B200WGCNA_DEVICE", "LOCAL_RANK"):
+        v = os.environ.get(var)
+        if v is not None and v != "":
+            return int(v)
+    return 0

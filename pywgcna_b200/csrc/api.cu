@@ -1,0 +1,278 @@
+// Host-pointer entry points of the C ABI (include/b200wgcna.h) and the error plumbing.
+// These are what pywgcna_b200/wgcna.py binds behind WGCNA.pickSoftThreshold / adjacency /
+// TOMsimilarity: H2D of the caller's float64 buffers, the dev_* kernels, D2H of the result.
+#include <stdarg.h>
+
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b200w {
+
+static thread_local std::string t_error;
+std::atomic<long long> g_launches{0};
+double g_last_kernel_ms = -1.0;
+
+void set_error(const std::string& msg) { t_error = msg; }
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  t_error = buf;
+  return code;
+}
+
+int ensure_device(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return fail(B200W_E_NO_DEVICE, "no CUDA device available (%s); libb200wgcna has no CPU path",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  }
+  if (device < 0 || device >= count)
+    return fail(B200W_E_INVALID, "device %d out of range (%d visible)", device, count);
+  static std::mutex mu;
+  static std::vector<int> major_of;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if ((int)major_of.size() != count) major_of.assign(count, -1);
+    if (major_of[device] < 0) {
+      int mj = 0;
+      if (cudaDeviceGetAttribute(&mj, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess)
+        return fail(B200W_E_CUDA, "cannot query device %d", device);
+      major_of[device] = mj;
+    }
+    if (major_of[device] != 10)
+      return fail(B200W_E_NO_DEVICE, "device %d is sm_%dx; this library is built for sm_100a only",
+                  device, major_of[device]);
+  }
+  B200W_CUDA(cudaSetDevice(device));
+  return 0;
+}
+
+// RAII device buffer + stream for the host entry points
+struct DevBuf {
+  void* p = nullptr;
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  template <class T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+struct Stream {
+  cudaStream_t s = nullptr;
+  cudaError_t create() { return cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking); }
+  ~Stream() {
+    if (s) cudaStreamDestroy(s);
+  }
+};
+
+}  // namespace b200w
+
+using namespace b200w;
+
+int b200w_dev_intramodular(const double* dA, int64_t n, const int32_t* d_labels,
+                           const uint8_t* d_small, double* d_total, double* d_within,
+                           cudaStream_t st);
+
+extern "C" int b200w_version(void) { return B200W_VERSION; }
+extern "C" const char* b200w_last_error(void) { return t_error.c_str(); }
+extern "C" int64_t b200w_launch_count(void) { return (int64_t)g_launches.load(); }
+extern "C" double b200w_last_kernel_ms(void) { return g_last_kernel_ms; }
+
+extern "C" int b200w_device_count(void) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int ok = 0;
+  for (int d = 0; d < count; ++d) {
+    int mj = 0;
+    if (cudaDeviceGetAttribute(&mj, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && mj == 10)
+      ++ok;
+  }
+  return ok;
+}
+
+extern "C" int b200w_connectivity_sweep(const double* X, int64_t m, int64_t n, const double* steps,
+                                        int P, int net_type, double* k_out, uint8_t* bad_out,
+                                        int device) {
+  if (!X || !steps || !k_out || m < 1 || n < 1 || P < 1)
+    return fail(B200W_E_INVALID, "connectivity_sweep: bad args");
+  if (int e = ensure_device(device)) return e;
+  Stream st;
+  B200W_CUDA(st.create());
+  DevBuf dX, dZ, dBad, dK;
+  const int64_t ldk = b200w_padded_k(m);
+  B200W_CUDA(dX.alloc((size_t)m * n * 8));
+  B200W_CUDA(dZ.alloc((size_t)n * ldk * 8));
+  B200W_CUDA(dBad.alloc((size_t)n));
+  B200W_CUDA(dK.alloc((size_t)P * n * 8));
+  B200W_CUDA(cudaMemcpyAsync(dX.p, X, (size_t)m * n * 8, cudaMemcpyHostToDevice, st.s));
+  if (int e = b200w_dev_standardize(dX.as<double>(), m, n, dZ.as<double>(), dBad.as<uint8_t>(),
+                                    device, st.s))
+    return e;
+  if (int e = b200w_dev_sweep(dZ.as<double>(), dBad.as<uint8_t>(), m, n, steps, P, net_type, 0, n,
+                              dK.as<double>(), device, st.s))
+    return e;
+  B200W_CUDA(cudaMemcpyAsync(k_out, dK.p, (size_t)P * n * 8, cudaMemcpyDeviceToHost, st.s));
+  if (bad_out) B200W_CUDA(cudaMemcpyAsync(bad_out, dBad.p, (size_t)n, cudaMemcpyDeviceToHost, st.s));
+  B200W_CUDA(cudaStreamSynchronize(st.s));
+  return 0;
+}
+
+extern "C" int b200w_adjacency(const double* X, int64_t m, int64_t n, int net_type, double power,
+                               int64_t row0, int64_t nrows, double* A_out, int device) {
+  if (!X || !A_out || m < 1 || n < 1 || row0 < 0 || nrows < 1 || row0 + nrows > n)
+    return fail(B200W_E_INVALID, "adjacency: bad args");
+  if (int e = ensure_device(device)) return e;
+  Stream st;
+  B200W_CUDA(st.create());
+  DevBuf dX, dZ, dBad, dA;
+  const int64_t ldk = b200w_padded_k(m);
+  B200W_CUDA(dX.alloc((size_t)m * n * 8));
+  B200W_CUDA(dZ.alloc((size_t)n * ldk * 8));
+  B200W_CUDA(dBad.alloc((size_t)n));
+  B200W_CUDA(dA.alloc((size_t)nrows * n * 8));
+  B200W_CUDA(cudaMemcpyAsync(dX.p, X, (size_t)m * n * 8, cudaMemcpyHostToDevice, st.s));
+  if (int e = b200w_dev_standardize(dX.as<double>(), m, n, dZ.as<double>(), dBad.as<uint8_t>(),
+                                    device, st.s))
+    return e;
+  if (int e = b200w_dev_adjacency(dZ.as<double>(), dBad.as<uint8_t>(), m, n, net_type, power, row0,
+                                  nrows, dA.as<double>(), device, st.s))
+    return e;
+  B200W_CUDA(cudaMemcpyAsync(A_out, dA.p, (size_t)nrows * n * 8, cudaMemcpyDeviceToHost, st.s));
+  B200W_CUDA(cudaStreamSynchronize(st.s));
+  return 0;
+}
+
+extern "C" int b200w_check_adjacency(const double* A, int64_t n, double* stats, int device) {
+  if (!A || !stats || n < 1) return fail(B200W_E_INVALID, "check_adjacency: bad args");
+  if (int e = ensure_device(device)) return e;
+  Stream st;
+  B200W_CUDA(st.create());
+  DevBuf dA, dS;
+  B200W_CUDA(dA.alloc((size_t)n * n * 8));
+  B200W_CUDA(dS.alloc(4 * 8));
+  B200W_CUDA(cudaMemcpyAsync(dA.p, A, (size_t)n * n * 8, cudaMemcpyHostToDevice, st.s));
+  if (int e = b200w_dev_check_adjacency(dA.as<double>(), n, dS.as<double>(), device, st.s)) return e;
+  B200W_CUDA(cudaMemcpyAsync(stats, dS.p, 4 * 8, cudaMemcpyDeviceToHost, st.s));
+  B200W_CUDA(cudaStreamSynchronize(st.s));
+  return 0;
+}
+
+// shared tail of b200w_tom / b200w_network: dA holds the full n x n adjacency on the device
+static int tom_from_device_adjacency(const double* dA, int64_t n, int tom_type, int tom_denom,
+                                     int out_mode, int precision, int64_t row0, int64_t nrows,
+                                     double* out_host, int device, cudaStream_t s) {
+  DevBuf dOp, dScale, dK, dOut;
+  precision = resolve_precision(precision);
+  B200W_CUDA(dOp.alloc((size_t)b200w_tom_operand_bytes(n, precision)));
+  B200W_CUDA(dScale.alloc((size_t)n * 8));
+  B200W_CUDA(dK.alloc((size_t)n * 8));
+  B200W_CUDA(dOut.alloc((size_t)nrows * n * 8));
+  if (int e = b200w_dev_tom_prepare(dA, n, 0, n, precision, dOp.p, dScale.as<double>(),
+                                    dK.as<double>(), device, s))
+    return e;
+  if (int e = b200w_dev_tom_compute(dA + row0 * n, dOp.p, dScale.as<double>(), dK.as<double>(), n,
+                                    row0, nrows, tom_type, tom_denom, out_mode, precision,
+                                    dOut.as<double>(), device, s))
+    return e;
+  B200W_CUDA(cudaMemcpyAsync(out_host, dOut.p, (size_t)nrows * n * 8, cudaMemcpyDeviceToHost, s));
+  B200W_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+extern "C" int b200w_tom(const double* A, int64_t n, int tom_type, int tom_denom, int out_mode,
+                         int precision, int64_t row0, int64_t nrows, double* out, int check,
+                         double* stats4, int device) {
+  if (!A || !out || n < 1 || row0 < 0 || nrows < 1 || row0 + nrows > n)
+    return fail(B200W_E_INVALID, "tom: bad args");
+  if (tom_type < 0 || tom_type > 1) return fail(B200W_E_INVALID, "tom: bad TOM type");
+  if (int e = ensure_device(device)) return e;
+  Stream st;
+  B200W_CUDA(st.create());
+  DevBuf dA;
+  B200W_CUDA(dA.alloc((size_t)n * n * 8));
+  B200W_CUDA(cudaMemcpyAsync(dA.p, A, (size_t)n * n * 8, cudaMemcpyHostToDevice, st.s));
+  if (check) {
+    DevBuf dS;
+    double hs[4];
+    B200W_CUDA(dS.alloc(4 * 8));
+    if (int e = b200w_dev_check_adjacency(dA.as<double>(), n, dS.as<double>(), device, st.s)) return e;
+    B200W_CUDA(cudaMemcpyAsync(hs, dS.p, 4 * 8, cudaMemcpyDeviceToHost, st.s));
+    B200W_CUDA(cudaStreamSynchronize(st.s));
+    if (stats4) for (int i = 0; i < 4; ++i) stats4[i] = hs[i];
+    if (hs[3] == 0.0) {  // any NaN makes np.max / np.min NaN and both comparisons False
+      if (hs[0] > 1e-12) return B200W_CHECK_ASYMMETRIC;
+      const double lo = (tom_type == B200W_TOM_SIGNED) ? -1.0 : 0.0;
+      if (hs[1] < lo || hs[2] > 1.0) return B200W_CHECK_RANGE;
+    }
+  }
+  return tom_from_device_adjacency(dA.as<double>(), n, tom_type, tom_denom, out_mode, precision,
+                                   row0, nrows, out, device, st.s);
+}
+
+extern "C" int b200w_network(const double* X, int64_t m, int64_t n, int net_type, double power,
+                             int tom_type, int tom_denom, int out_mode, int precision,
+                             double* A_out, double* tom_out, int device) {
+  if (!X || !tom_out || m < 1 || n < 1) return fail(B200W_E_INVALID, "network: bad args");
+  if (int e = ensure_device(device)) return e;
+  Stream st;
+  B200W_CUDA(st.create());
+  DevBuf dX, dZ, dBad, dA;
+  const int64_t ldk = b200w_padded_k(m);
+  B200W_CUDA(dX.alloc((size_t)m * n * 8));
+  B200W_CUDA(dZ.alloc((size_t)n * ldk * 8));
+  B200W_CUDA(dBad.alloc((size_t)n));
+  B200W_CUDA(dA.alloc((size_t)n * n * 8));
+  B200W_CUDA(cudaMemcpyAsync(dX.p, X, (size_t)m * n * 8, cudaMemcpyHostToDevice, st.s));
+  if (int e = b200w_dev_standardize(dX.as<double>(), m, n, dZ.as<double>(), dBad.as<uint8_t>(),
+                                    device, st.s))
+    return e;
+  if (int e = b200w_dev_adjacency(dZ.as<double>(), dBad.as<uint8_t>(), m, n, net_type, power, 0, n,
+                                  dA.as<double>(), device, st.s))
+    return e;
+  if (A_out)
+    B200W_CUDA(cudaMemcpyAsync(A_out, dA.p, (size_t)n * n * 8, cudaMemcpyDeviceToHost, st.s));
+  return tom_from_device_adjacency(dA.as<double>(), n, tom_type, tom_denom, out_mode, precision, 0,
+                                   n, tom_out, device, st.s);
+}
+
+extern "C" int b200w_intramodular(const double* A, int64_t n, const int32_t* labels, int nmod,
+                                  const uint8_t* small, double* k_total, double* k_within,
+                                  int device) {
+  if (!A || !labels || !small || !k_total || !k_within || n < 1 || nmod < 1)
+    return fail(B200W_E_INVALID, "intramodular: bad args");
+  for (int64_t i = 0; i < n; ++i)
+    if (labels[i] < 0 || labels[i] >= nmod)
+      return fail(B200W_E_INVALID, "intramodular: label %d out of range", (int)labels[i]);
+  if (int e = ensure_device(device)) return e;
+  Stream st;
+  B200W_CUDA(st.create());
+  DevBuf dA, dL, dS, dT, dW;
+  B200W_CUDA(dA.alloc((size_t)n * n * 8));
+  B200W_CUDA(dL.alloc((size_t)n * 4));
+  B200W_CUDA(dS.alloc((size_t)nmod));
+  B200W_CUDA(dT.alloc((size_t)n * 8));
+  B200W_CUDA(dW.alloc((size_t)n * 8));
+  B200W_CUDA(cudaMemcpyAsync(dA.p, A, (size_t)n * n * 8, cudaMemcpyHostToDevice, st.s));
+  B200W_CUDA(cudaMemcpyAsync(dL.p, labels, (size_t)n * 4, cudaMemcpyHostToDevice, st.s));
+  B200W_CUDA(cudaMemcpyAsync(dS.p, small, (size_t)nmod, cudaMemcpyHostToDevice, st.s));
+  if (int e = b200w_dev_intramodular(dA.as<double>(), n, dL.as<int32_t>(), dS.as<uint8_t>(),
+                                     dT.as<double>(), dW.as<double>(), st.s))
+    return e;
+  B200W_CUDA(cudaMemcpyAsync(k_total, dT.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st.s));
+  B200W_CUDA(cudaMemcpyAsync(k_within, dW.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st.s));
+  B200W_CUDA(cudaStreamSynchronize(st.s));
+  return 0;
+}

@@ -1,0 +1,274 @@
+// Topological-overlap side of the hot path: checkAdjMat reductions, operand preparation,
+// the FP64 (DMMA) contraction + TOM epilogue, intramodular connectivity.
+// Reference: PyWGCNA/wgcna.py:1114-1138 (checkAdjMat), :1141-1157 (TomSimilarityFromAdj),
+// :1160-1193 (TOMsimilarity), :3403-3450 (intramodularConnectivity).
+#include "gemm_f64.cuh"
+#include "tom_common.cuh"
+
+namespace b200w {
+
+// -------------------------------------------------------------------------------------------
+// checkAdjMat reductions (wgcna.py:1135-1138): max|A - A^T|, min, max, NaN count in one pass.
+// Each CTA handles one 32 x 32 tile pair (bi <= bj): it reads tile (bi,bj) and tile (bj,bi), both
+// row-wise (coalesced), transposes the second through shared memory.  Per-CTA partials are reduced
+// by a second kernel in fixed order.
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+check_adj_kernel(const double* __restrict__ A, int64_t n, int64_t tiles, double* __restrict__ part) {
+  __shared__ double tb[32][33];
+  __shared__ double red[4][8];
+  // triangular tile index -> (bi, bj), bi <= bj
+  int64_t t = blockIdx.x;
+  int64_t bi = (int64_t)floor((2.0 * tiles + 1.0 - sqrt((2.0 * tiles + 1.0) * (2.0 * tiles + 1.0) - 8.0 * (double)t)) / 2.0);
+  while (bi > 0 && bi * tiles - bi * (bi - 1) / 2 > t) --bi;
+  while ((bi + 1) * tiles - (bi + 1) * bi / 2 <= t) ++bi;
+  int64_t bj = bi + (t - (bi * tiles - bi * (bi - 1) / 2));
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+
+  double asym = 0.0, mn = INFINITY, mx = -INFINITY, nans = 0.0;
+  for (int r = ty; r < 32; r += 8) {  // tile (bj, bi) rows
+    int64_t i = bj * 32 + r, j = bi * 32 + tx;
+    tb[r][tx] = (i < n && j < n) ? A[i * n + j] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    int64_t i = bi * 32 + r, j = bj * 32 + tx;
+    if (i < n && j < n) {
+      double a = A[i * n + j], b = tb[tx][r];
+      asym = fmax(asym, fabs(a - b));  // fmax drops a NaN operand
+      if (isnan(a)) nans += 1.0; else { mn = fmin(mn, a); mx = fmax(mx, a); }
+      if (bi != bj) { if (isnan(b)) nans += 1.0; else { mn = fmin(mn, b); mx = fmax(mx, b); } }
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    asym = fmax(asym, __shfl_xor_sync(0xffffffffu, asym, o));
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    nans += __shfl_xor_sync(0xffffffffu, nans, o);
+  }
+  if (tx == 0) { red[0][ty] = asym; red[1][ty] = mn; red[2][ty] = mx; red[3][ty] = nans; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) {
+      asym = fmax(asym, red[0][w]); mn = fmin(mn, red[1][w]); mx = fmax(mx, red[2][w]);
+      nans += red[3][w];
+    }
+    double* o = part + (int64_t)blockIdx.x * 4;
+    o[0] = asym; o[1] = mn; o[2] = mx; o[3] = nans;
+  }
+}
+
+__global__ void check_adj_reduce_kernel(const double* __restrict__ part, int64_t nb,
+                                        double* __restrict__ stats) {
+  __shared__ double red[4][256];
+  double asym = 0.0, mn = INFINITY, mx = -INFINITY, nans = 0.0;
+  for (int64_t b = threadIdx.x; b < nb; b += blockDim.x) {
+    asym = fmax(asym, part[b * 4]); mn = fmin(mn, part[b * 4 + 1]);
+    mx = fmax(mx, part[b * 4 + 2]); nans += part[b * 4 + 3];
+  }
+  red[0][threadIdx.x] = asym; red[1][threadIdx.x] = mn; red[2][threadIdx.x] = mx;
+  red[3][threadIdx.x] = nans;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)blockDim.x; ++i) {
+      asym = fmax(asym, red[0][i]); mn = fmin(mn, red[1][i]); mx = fmax(mx, red[2][i]);
+      nans += red[3][i];
+    }
+    stats[0] = asym; stats[1] = mn; stats[2] = mx; stats[3] = nans;
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// Operand preparation, FP64 flavour: one CTA per row.  Ac[i, :] = A[i, :] with NaN -> 0
+// (wgcna.py:1185) and the diagonal zeroed (:1143), zero padded to ldn; k_i = sum_j Ac[i, j] (:1146).
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tom_prepare_f64_kernel(const double* __restrict__ A_rows, int64_t n, int64_t ldn, int64_t row0,
+                       double* __restrict__ Ac, double* __restrict__ k) {
+  const int64_t i = row0 + blockIdx.x;
+  const double* src = A_rows + (int64_t)blockIdx.x * n;
+  double* dst = Ac + i * ldn;
+  double s = 0.0;
+  for (int64_t j = threadIdx.x; j < ldn; j += 256) {
+    double a = 0.0;
+    if (j < n) a = tom_clean(src[j], i, j);
+    dst[j] = a;
+    s += a;
+  }
+  s = block_sum_256(s);
+  if (threadIdx.x == 0) k[i] = s;
+}
+
+// -------------------------------------------------------------------------------------------
+// K4 (FP64 flavour): L = Ac[rows] * Ac^T on the DMMA pipe (A symmetric to 1e-12, checkAdjMat),
+// epilogue (L + a) / (min(k_i, k_j) + 1 - a) etc. while the tile is in registers.
+// 1-D grid, row tiles grouped by 8 so that concurrently resident CTAs share operand panels in L2.
+// -------------------------------------------------------------------------------------------
+constexpr int kTomStages = 4;
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+tom_f64_kernel(const double* __restrict__ A_rows, const double* __restrict__ Ac,
+               const double* __restrict__ k, int64_t n, int64_t ldn, int64_t row0, int64_t nrows,
+               int tom_type, int tom_denom, int out_mode, double* __restrict__ out) {
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, tig = lane & 3;
+  const int64_t tiles_m = (nrows + kBM - 1) / kBM, tiles_n = (n + kBN - 1) / kBN;
+  int64_t tm, tn;
+  grouped_tile(blockIdx.x, tiles_m, tiles_n, 8, tm, tn);
+  const int64_t i0 = row0 + tm * kBM, j0 = tn * kBN, iend = row0 + nrows;
+
+  AccF64 acc;
+  acc.clear();
+  gemm_f64_tile<kTomStages>(acc, smem, Ac, Ac, ldn, ldn, i0, n, j0, n);
+
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi) {
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      const int64_t gi = i0 + wm * 64 + mi * 16 + g + ch * 8;
+      if (gi >= iend) continue;
+      const double ki = k[gi];
+      const double* arow = A_rows + (gi - row0) * n;
+      double* orow = out + (gi - row0) * n;
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb) {
+          const int64_t gj = j0 + wn * 32 + ni * 8 + 2 * tig + cb;
+          if (gj >= n) continue;
+          const double a = tom_clean(arow[gj], gi, gj);
+          orow[gj] = tom_value(acc.v[mi][ni][ch * 2 + cb], a, ki, k[gj], gi == gj, tom_type,
+                               tom_denom, out_mode);
+        }
+      }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------
+// intramodularConnectivity (wgcna.py:3431-3445): one CTA per row, HBM-bound segmented row sum.
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+intramodular_kernel(const double* __restrict__ A, int64_t n, const int32_t* __restrict__ labels,
+                    const uint8_t* __restrict__ small, double* __restrict__ k_total,
+                    double* __restrict__ k_within) {
+  const int64_t i = blockIdx.x;
+  const int32_t li = labels[i];
+  const double* row = A + i * n;
+  double st = 0.0, sw = 0.0;
+  for (int64_t j = threadIdx.x; j < n; j += 256) {
+    double a = tom_clean(row[j], i, j);
+    st += a;
+    if (labels[j] == li) sw += a;
+  }
+  st = block_sum_256(st);
+  sw = block_sum_256(sw);
+  if (threadIdx.x == 0) {
+    k_total[i] = st;
+    k_within[i] = small[li] ? 0.0 : sw;
+  }
+}
+
+}  // namespace b200w
+
+using namespace b200w;
+
+extern "C" int64_t b200w_padded_n(int64_t n) { return round_up(n, 128); }
+
+extern "C" int64_t b200w_tom_operand_bytes(int64_t n, int precision) {
+  const int64_t ldn = b200w_padded_n(n);
+  // rows are padded to a whole number of 128-row operand tiles as well, so that TMA boxes of the
+  // int8 path never start outside the tensor
+  const int64_t rows = round_up(n, 128);
+  if (precision == B200W_PREC_F64) return rows * ldn * 8;
+  return (int64_t)B200W_I8_SLICES * rows * ldn;
+}
+
+extern "C" int b200w_dev_check_adjacency(const double* dA, int64_t n, double* d_stats4, int device,
+                                         void* stream) {
+  if (!dA || !d_stats4 || n < 1) return fail(B200W_E_INVALID, "check_adjacency: bad args");
+  if (int e = ensure_device(device)) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t tiles = (n + 31) / 32, nb = tiles * (tiles + 1) / 2;
+  if (nb > 2147483647LL) return fail(B200W_E_UNSUPPORTED, "check_adjacency: n too large");
+  Scratch part;
+  B200W_CUDA(part.alloc((size_t)nb * 4 * sizeof(double), st));
+  check_adj_kernel<<<(unsigned)nb, 256, 0, st>>>(dA, n, tiles, part.as<double>());
+  B200W_LAUNCHED();
+  check_adj_reduce_kernel<<<1, 256, 0, st>>>(part.as<double>(), nb, d_stats4);
+  B200W_LAUNCHED();
+  return 0;
+}
+
+int b200w_tom_prepare_i8(const double* dA_rows, int64_t n, int64_t row0, int64_t nrows,
+                         void* d_operand, double* d_scale, double* d_k, cudaStream_t st);
+int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, const double* d_scale,
+                         const double* d_k, int64_t n, int64_t row0, int64_t nrows, int tom_type,
+                         int tom_denom, int out_mode, double* d_out, cudaStream_t st);
+
+int b200w::resolve_precision(int precision) {
+  if (precision == B200W_PREC_AUTO) return B200W_PREC_F64;  // TODO(i8): flip once tom_i8 is parity-green
+  return precision;
+}
+
+extern "C" int b200w_dev_tom_prepare(const double* dA_rows, int64_t n, int64_t row0, int64_t nrows,
+                                     int precision, void* d_operand, double* d_scale, double* d_k,
+                                     int device, void* stream) {
+  if (!dA_rows || !d_operand || !d_k || n < 1 || row0 < 0 || nrows < 1 || row0 + nrows > n)
+    return fail(B200W_E_INVALID, "tom_prepare: bad args");
+  precision = resolve_precision(precision);
+  if (int e = ensure_device(device)) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == B200W_PREC_F64) {
+    tom_prepare_f64_kernel<<<(unsigned)nrows, 256, 0, st>>>(dA_rows, n, b200w_padded_n(n), row0,
+                                                            (double*)d_operand, d_k);
+    B200W_LAUNCHED();
+    return 0;
+  }
+  if (precision == B200W_PREC_I8) {
+    if (!d_scale) return fail(B200W_E_INVALID, "tom_prepare: i8 needs d_scale");
+    return b200w_tom_prepare_i8(dA_rows, n, row0, nrows, d_operand, d_scale, d_k, st);
+  }
+  return fail(B200W_E_INVALID, "tom_prepare: unknown precision %d", precision);
+}
+
+extern "C" int b200w_dev_tom_compute(const double* dA_rows, const void* d_operand,
+                                     const double* d_scale, const double* d_k, int64_t n,
+                                     int64_t row0, int64_t nrows, int tom_type, int tom_denom,
+                                     int out_mode, int precision, double* d_out, int device,
+                                     void* stream) {
+  if (!dA_rows || !d_operand || !d_k || !d_out || n < 1 || row0 < 0 || nrows < 1 ||
+      row0 + nrows > n)
+    return fail(B200W_E_INVALID, "tom_compute: bad args");
+  if (tom_type < 0 || tom_type > 1 || tom_denom < 0 || tom_denom > 1 || out_mode < 0 || out_mode > 2)
+    return fail(B200W_E_INVALID, "tom_compute: bad enum");
+  precision = resolve_precision(precision);
+  if (int e = ensure_device(device)) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == B200W_PREC_F64) {
+    const size_t smem = gemm_smem_bytes(kTomStages);
+    B200W_CUDA(cudaFuncSetAttribute(tom_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
+    const int64_t tiles = ((nrows + kBM - 1) / kBM) * ((n + kBN - 1) / kBN);
+    tom_f64_kernel<<<(unsigned)tiles, kGemmThreads, smem, st>>>(
+        dA_rows, (const double*)d_operand, d_k, n, b200w_padded_n(n), row0, nrows, tom_type,
+        tom_denom, out_mode, d_out);
+    B200W_LAUNCHED();
+    return 0;
+  }
+  if (precision == B200W_PREC_I8) {
+    if (!d_scale) return fail(B200W_E_INVALID, "tom_compute: i8 needs d_scale");
+    return b200w_tom_compute_i8(dA_rows, d_operand, d_scale, d_k, n, row0, nrows, tom_type,
+                                tom_denom, out_mode, d_out, st);
+  }
+  return fail(B200W_E_INVALID, "tom_compute: unknown precision %d", precision);
+}
+
+int b200w_dev_intramodular(const double* dA, int64_t n, const int32_t* d_labels,
+                           const uint8_t* d_small, double* d_total, double* d_within,
+                           cudaStream_t st) {
+  intramodular_kernel<<<(unsigned)n, 256, 0, st>>>(dA, n, d_labels, d_small, d_total, d_within);
+  B200W_LAUNCHED();
+  return 0;
+}

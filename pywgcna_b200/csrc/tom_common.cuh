@@ -1,0 +1,59 @@
+// Pieces shared by the FP64 and int8 TOM kernels.
+#pragma once
+#include "common.cuh"
+
+namespace b200w {
+
+#ifdef __CUDACC__
+// np.nan_to_num (wgcna.py:1185; default also maps +-inf to +-DBL_MAX, unreachable for a matrix that
+// passed checkAdjMat) and fill_diagonal(A, 0) (wgcna.py:1143)
+__device__ __forceinline__ double tom_clean(double a, int64_t i, int64_t j) {
+  return (i == j || isnan(a)) ? 0.0 : a;
+}
+
+// TomSimilarityFromAdj element, wgcna.py:1148-1156, plus the 1 - TOM / round(8) hand-off of
+// findModules (wgcna.py:323-324).  L = (A @ A)[i, j], a = cleaned A[i, j].
+__device__ __forceinline__ double tom_value(double L, double a, double ki, double kj, bool diag,
+                                            int tom_type, int tom_denom, int out_mode) {
+  double t;
+  if (diag) {
+    t = 1.0;  // wgcna.py:1156
+  } else {
+    const double D = (tom_denom == B200W_DENOM_MIN) ? fmin(ki, kj) : (ki + kj) / 2.0;
+    if (tom_type == B200W_TOM_UNSIGNED) t = (L + a) / (D + 1.0 - a);  // :1153
+    else t = fabs(L + a) / (D + 1.0 - fabs(a));                       // :1155
+  }
+  if (out_mode == B200W_OUT_TOM) return t;
+  t = 1.0 - t;
+  if (out_mode == B200W_OUT_DISS_R8) t = rint(t * 1e8) / 1e8;  // numpy around(decimals=8)
+  return t;
+}
+
+__device__ __forceinline__ double block_sum_256(double v) {
+  __shared__ double red_[8];
+  __syncthreads();  // protect red_ across consecutive calls
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red_[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = red_[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) s += red_[w];
+  return s;
+}
+
+// 1-D tile index -> (tm, tn) with row tiles taken in groups of `group`, column index fastest inside
+// a group's row: concurrently resident CTAs then cover a compact block of the output and share
+// operand panels in L2.
+__device__ __forceinline__ void grouped_tile(int64_t pid, int64_t tiles_m, int64_t tiles_n,
+                                             int group, int64_t& tm, int64_t& tn) {
+  const int64_t per_group = (int64_t)group * tiles_n;
+  const int64_t gid = pid / per_group;
+  const int64_t first_m = gid * group;
+  const int64_t gsz = (tiles_m - first_m < group) ? tiles_m - first_m : group;
+  const int64_t r = pid % per_group;
+  tm = first_m + r % gsz;
+  tn = r / gsz;
+}
+#endif
+
+}  // namespace b200w

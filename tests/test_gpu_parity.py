@@ -1,0 +1,207 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes, pywgcna_b200/wgcna.py),
+against (a) golden outputs of the unmodified reference and (b) the numpy oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): max-abs <= 1e-6 on correlation / adjacency / TOM and the
+identical selected power.  The FP64 kernels are held to a much tighter bound (1e-11); the int8-slice
+TOM to 1e-9 (39-bit fixed point, exact accumulation)."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import pywgcna_b200 as bw
+from oracle import restated as O
+from pywgcna_b200 import _lib
+from pywgcna_b200.synth import make_expression
+
+pytestmark = pytest.mark.gpu
+
+NETS = ["unsigned", "signed", "signed hybrid"]
+CASES = ["pipeline_small", "pipeline_ragged", "pipeline_edge"]
+TOL_NORTH_STAR = 1e-6
+TOL_F64 = 1e-11
+TOL_TOM = {"f64": 1e-11, "i8": 1e-9}
+PRECISIONS = ["f64", "i8"]
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+def maxabs(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    assert a.shape == b.shape
+    assert np.array_equal(np.isnan(a), np.isnan(b)), "NaN pattern differs"
+    with np.errstate(invalid="ignore"):
+        return float(np.nanmax(np.abs(a - b))) if a.size else 0.0
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("net", NETS)
+def test_golden_soft_threshold(gpu, golden_dir, case, net):
+    g = load(golden_dir, case)
+    key = net.replace(" ", "_")
+    p, sft = bw.pickSoftThreshold(pd.DataFrame(g["X"]), networkType=net, powerVector=list(g["powers"]))
+    assert isinstance(p, np.int64) and int(p) == int(g[f"power_{key}"])
+    assert list(sft.columns) == O.SFT_COLUMNS and sft.shape == g[f"sft_{key}"].shape
+    got, ref = sft.to_numpy(dtype=float), g[f"sft_{key}"]
+    assert np.array_equal(got[:, 0], ref[:, 0])
+    # connectivity columns: relative 1e-10; fit columns: the 10-point OLS amplifies k's last bits
+    np.testing.assert_allclose(got[:, 4:], ref[:, 4:], rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(got[:, 1:4], ref[:, 1:4], rtol=1e-7, atol=1e-8)
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("net", NETS)
+def test_golden_adjacency(gpu, golden_dir, case, net):
+    g = load(golden_dir, case)
+    key = net.replace(" ", "_")
+    A = bw.adjacency(pd.DataFrame(g["X"]), adjacencyType=net, power=6)
+    assert isinstance(A, np.ndarray) and A.dtype == np.float64 and A.flags.c_contiguous and A.flags.writeable
+    assert maxabs(A, g[f"adj_{key}"]) < TOL_F64
+    finite = np.nan_to_num(A)
+    assert np.array_equal(finite, finite.T), "adjacency must be exactly symmetric (checkAdjMat 1e-12)"
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+@pytest.mark.parametrize("case", CASES)
+def test_golden_tom(gpu, golden_dir, case, prec):
+    g = load(golden_dir, case)
+    for net in NETS:
+        key = net.replace(" ", "_")
+        for tt in ["unsigned", "signed"]:
+            for td in ["min", "mean"]:
+                A = g[f"adj_{key}"].copy()
+                T = bw.TOMsimilarity(A, TOMType=tt, TOMDenom=td, precision=prec)
+                assert isinstance(T, pd.DataFrame) and isinstance(T.index, pd.RangeIndex)
+                assert maxabs(T.to_numpy(), g[f"tom_{key}_{tt}_{td}"]) < TOL_TOM[prec], (net, tt, td)
+                # in-place side effects of the reference on a writable input (wgcna.py:1185, :1143)
+                assert not np.isnan(A).any() and np.all(np.diag(A) == 0)
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_golden_signed_user_adjacency(gpu, golden_dir, prec):
+    g = load(golden_dir, "tom_signed_user")
+    for td in ["min", "mean"]:
+        T = bw.TOMsimilarity(g["A"].copy(), TOMType="signed", TOMDenom=td, precision=prec).to_numpy()
+        assert maxabs(T, g[f"tom_signed_{td}"]) < TOL_TOM[prec]
+        T = bw.TOMsimilarity(g["Apos"].copy(), TOMType="unsigned", TOMDenom=td, precision=prec).to_numpy()
+        assert maxabs(T, g[f"tom_unsigned_{td}"]) < TOL_TOM[prec]
+    # a negative entry is out of range for the unsigned TOM (wgcna.py:1137-1138)
+    with pytest.raises(SystemExit):
+        bw.TOMsimilarity(g["A"].copy(), TOMType="unsigned")
+
+
+def test_golden_intramodular(gpu, golden_dir):
+    g = load(golden_dir, "tom_signed_user")
+    imc = bw.intramodularConnectivity(g["Apos"].copy(), g["imc_colors"])
+    assert list(imc.columns) == ["kTotal", "kWithin", "kOut", "kDiff"]
+    assert maxabs(imc.to_numpy(), g["imc"]) < 1e-11
+
+
+def test_check_adjmat(gpu):
+    rng = np.random.default_rng(5)
+    B = rng.random((77, 77))
+    A = (B + B.T) / 2
+    bw.checkAdjMat(A)
+    bad = A.copy()
+    bad[3, 10] += 1e-9
+    with pytest.raises(SystemExit) as e:
+        bw.checkAdjMat(bad)
+    assert "not symmetric" in str(e.value)
+    with pytest.raises(SystemExit):
+        bw.checkAdjMat(A * 3)
+    with pytest.raises(SystemExit):
+        bw.TOMsimilarity(bad)
+    nan = bad.copy()
+    nan[0, 1] = np.nan  # numpy: max/min are NaN -> both comparisons False -> passes
+    bw.checkAdjMat(nan)
+    O.checkAdjMat(nan)
+
+
+@pytest.mark.parametrize("net", NETS)
+@pytest.mark.parametrize("m,n", [(50, 1000), (200, 3001), (33, 130)])
+def test_oracle_sweep_adjacency(gpu, net, m, n):
+    X = make_expression(m, n, F=8, seed=m + n)
+    df = pd.DataFrame(X)
+    powers = list(range(1, 21))
+    pv, datk_ref = O.connectivity_sweep(X, powers, net, faithful=False)
+    datk = bw.connectivity(df, powers, net)
+    np.testing.assert_allclose(datk, datk_ref, rtol=1e-11, atol=1e-11)
+    p, sft = bw.pickSoftThreshold(df, networkType=net, powerVector=powers)
+    p_ref = O.select_power(pv, O.sft_table(pv, datk_ref))
+    assert int(p) == int(p_ref)
+    A = bw.adjacency(df, adjacencyType=net, power=6)
+    assert maxabs(A, O.adjacency(df, adjacencyType=net, power=6)) < TOL_F64
+    # row blocks (multi-GPU sharding) reproduce the full matrix bit for bit
+    r0, nr = n // 3, n // 2
+    blk = bw.adjacency(df, adjacencyType=net, power=6, rows=(r0, nr))
+    assert np.array_equal(blk, A[r0:r0 + nr])
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+@pytest.mark.parametrize("n", [64, 1000, 2500])
+def test_oracle_tom(gpu, prec, n):
+    X = make_expression(80, n, F=6, seed=n)
+    for net, power in [("unsigned", 6), ("signed hybrid", 4), ("signed", 12)]:
+        A = O.adjacency(X, adjacencyType=net, power=power)
+        for tt, td in [("unsigned", "min"), ("signed", "mean")]:
+            T_ref = O.TOMsimilarity(A.copy(), TOMType=tt, TOMDenom=td).to_numpy()
+            T = bw.TOMsimilarity(A.copy(), TOMType=tt, TOMDenom=td, precision=prec).to_numpy()
+            assert maxabs(T, T_ref) < TOL_TOM[prec], (net, tt, td)
+            assert np.all(np.diag(T) == 1.0)
+    # row block == slice of the full result; fused dissTOM == (1 - TOM).round(8)
+    T = bw.TOMsimilarity(A.copy(), precision=prec).to_numpy()
+    blk = bw.wgcna._tom(A.copy(), 1, 0, check=False, rows=(n // 4, n // 2), precision=prec)
+    assert np.array_equal(blk, T[n // 4:n // 4 + n // 2])
+    D = bw.dissTOM(A.copy(), precision=prec)
+    assert np.array_equal(D, (1 - T).round(decimals=8))
+
+
+def test_fused_network_matches_two_calls(gpu):
+    X = make_expression(60, 900, F=5, seed=9)
+    A, T = bw.network(pd.DataFrame(X), power=6, networkType="signed hybrid", TOMType="signed")
+    A2 = bw.adjacency(pd.DataFrame(X), adjacencyType="signed hybrid", power=6)
+    T2 = bw.TOMsimilarity(A2.copy(), TOMType="signed")
+    assert np.array_equal(A, A2) and np.array_equal(T.to_numpy(), T2.to_numpy())
+
+
+def test_soft_connectivity(gpu):
+    X = make_expression(40, 300, F=4, seed=21)
+    for net in NETS:
+        k = bw.softConnectivity(pd.DataFrame(X), type=net, power=6)
+        np.testing.assert_allclose(k, O.softConnectivity(X, type=net, power=6), rtol=1e-11, atol=1e-11)
+    Xb = X.copy()
+    Xb[:, 7] = 1.0
+    assert np.isnan(bw.softConnectivity(pd.DataFrame(Xb))).all()
+    assert np.isnan(O.softConnectivity(Xb)).all()
+
+
+def test_properties_at_scale(gpu):
+    """Size-independent properties at a size the oracle cannot finish quickly."""
+    n, m = 6000, 120
+    X, mods = make_expression(m, n, F=20, seed=77, return_modules=True)
+    A = bw.adjacency(pd.DataFrame(X), adjacencyType="unsigned", power=6)
+    assert np.array_equal(A, A.T) and A.min() >= 0 and A.max() <= 1
+    assert np.all(np.abs(np.diag(A) - 1) < 1e-12)
+    # gene permutation equivariance
+    perm = np.random.default_rng(1).permutation(n)
+    Ap = bw.adjacency(pd.DataFrame(X[:, perm]), adjacencyType="unsigned", power=6)
+    assert np.max(np.abs(Ap - A[np.ix_(perm, perm)])) < 1e-12
+    # connectivity == row sums of the adjacency - 1
+    k = bw.connectivity(pd.DataFrame(X), [6], "unsigned")[:, 0]
+    np.testing.assert_allclose(k, A.sum(axis=1) - 1, rtol=1e-11)
+    for prec in PRECISIONS:
+        T = bw.TOMsimilarity(A.copy(), TOMType="unsigned", precision=prec).to_numpy()
+        assert np.max(np.abs(T - T.T)) < 1e-9 and T.min() >= 0 and T.max() <= 1 + 1e-12
+        assert np.all(np.diag(T) == 1)
+        # row-sampled check against float64 numpy (the oracle's formula on 40 rows)
+        rows = np.random.default_rng(2).choice(n, 40, replace=False)
+        A0 = A.copy()
+        np.fill_diagonal(A0, 0)
+        kk = A0.sum(axis=1)
+        Lr = A0[rows] @ A0
+        Tr = (Lr + A0[rows]) / (np.minimum(kk[rows][:, None], kk[None, :]) + 1 - A0[rows])
+        Tr[np.arange(len(rows)), rows] = 1
+        assert np.max(np.abs(T[rows] - Tr)) < TOL_TOM[prec]

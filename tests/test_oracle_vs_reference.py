@@ -1,0 +1,30 @@
+"""Live differential test: oracle restatement vs the unmodified reference, only where the reference
+tree exists (the build container).  On the GPU box it is skipped -- the goldens cover it there."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import ref_import as R
+from oracle import restated as O
+from pywgcna_b200.synth import make_expression
+
+pytestmark = pytest.mark.skipif(not R.reference_available(), reason="reference tree not present")
+
+
+@pytest.mark.parametrize("net", ["unsigned", "signed", "signed hybrid"])
+def test_pipeline_live(net):
+    X = make_expression(40, 220, F=5, seed=11)
+    df = pd.DataFrame(X)
+    powers = list(range(1, 11)) + list(range(11, 21, 2))
+    p_ref, sft_ref = R.ref_pickSoftThreshold(df, networkType=net, powerVector=powers)
+    p, sft = O.pickSoftThreshold(df, networkType=net, powerVector=powers)
+    assert int(p) == int(p_ref)
+    np.testing.assert_allclose(sft.to_numpy(dtype=float), sft_ref.to_numpy(dtype=float), rtol=1e-9, atol=1e-9)
+    # blocked (faithful) and one-shot correlation agree
+    _, sft2 = O.pickSoftThreshold(df, networkType=net, powerVector=powers, faithful=False, blockSize=64)
+    np.testing.assert_allclose(sft2.to_numpy(dtype=float), sft_ref.to_numpy(dtype=float), rtol=1e-9, atol=1e-9)
+    A_ref = R.ref_adjacency(df, adjacencyType=net, power=6)
+    np.testing.assert_allclose(O.adjacency(df, adjacencyType=net, power=6), A_ref, rtol=0, atol=1e-14)
+    for tt in ["unsigned", "signed"]:
+        T_ref = R.ref_TOMsimilarity(A_ref, TOMType=tt).to_numpy()
+        np.testing.assert_allclose(O.TOMsimilarity(A_ref.copy(), TOMType=tt).to_numpy(), T_ref, rtol=0, atol=1e-13)
