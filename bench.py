@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path of PyWGCNA network construction on B200 (contract in the task brief).
+
+A "step" is one pass of the hot path over one synthetic expression matrix that is already resident
+in HBM:  standardise -> fused soft-threshold sweep (all powers) -> k to the host, scale-free fit and
+power selection (host, 10 points per power) -> adjacency at the selected power -> TOM.
+Workload at every N: BASELINE.json configs[1] ("C2": 20 000 genes x 200 samples, signed hybrid,
+powers 1..20, signed TOM, min denominator); with N > 1 the rows of the adjacency / TOM and the sweep
+columns are sharded in contiguous row blocks (strong scaling), operand and k exchanged with NCCL.
+
+  python bench.py --gpus N --steps K --warmup W            (torchrun for N > 1)
+  python bench.py --impl reference ...                      CPU arm: the oracle port of the reference
+                                                            (oracle/restated.py) on a bounded sample
+
+One JSON line on stdout (rank 0).  metric: algorithmic TFLOP/s of the step,
+flops = 2mn^2 (sweep correlation) + 2Pn^2 (power chain) + 2mn^2 (adjacency correlation) + 2n^3 (A.A).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+os.environ.setdefault("B200WGCNA_QUIET", "1")
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (m, n, F, seed, networkType, TOMType, powers)
+    "C2": (200, 20000, 40, 20200, "signed hybrid", "signed", list(range(1, 21))),
+    "C3": (500, 50000, 60, 50500, "unsigned", "unsigned", list(range(1, 21))),
+    "C4": (5000, 30000, 60, 305000, "signed", "signed", list(range(1, 21))),
+    "tiny": (60, 1500, 6, 7, "signed hybrid", "signed", list(range(1, 21))),
+}
+METRIC = "TOMsimilarity+softThreshold TFLOP/s (sweep + adjacency + TOM, algorithmic flops)"
+
+
+def step_flops(m, n, P):
+    return 2.0 * m * n * n + 2.0 * P * n * n + 2.0 * m * n * n + 2.0 * n ** 3
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="auto", choices=["auto", "f64", "i8"])
+    ap.add_argument("--cpu-sample-genes", type=int, default=3000)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md clocks line)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [l for (t, l) in self.lines if t0 - 0.05 <= t <= t1 + 0.15] or [l for _, l in self.lines]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in rows:
+            f = [x.strip() for x in l.split(",")]
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except Exception:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: oracle port of the reference on a bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_step(X, net, tom_type, powers):
+    """One pass of the reference's CPU algorithm (oracle/restated.py, which follows wgcna.py line by
+    line incl. the blocked np.corrcoef of :882) -- sweep, adjacency at the selected power, TOM."""
+    import pandas as pd
+
+    from oracle import restated as O
+
+    df = pd.DataFrame(X)
+    power, _ = O.pickSoftThreshold(df, networkType=net, powerVector=powers, faithful=True)
+    A = O.adjacency(df, adjacencyType=net, power=power)
+    T = O.TOMsimilarity(A, TOMType=tom_type)
+    return float(T.iloc[0, 1])
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+
+        n = [p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"]
+        return max(n) if n else os.cpu_count()
+    except Exception:
+        return os.cpu_count()
+
+
+def cpu_baseline(wl, genes, reps=1):
+    from pywgcna_b200.synth import make_expression
+
+    m, n, F, seed, net, tom_type, powers = WORKLOADS[wl]
+    ns = min(n, genes)
+    X = make_expression(m, ns, F=F, seed=seed)
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cpu_step(X, net, tom_type, powers)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": step_flops(m, ns, len(powers)) / best / 1e12, "unit": "TFLOP/s", "cores": cpu_threads(),
+            "kind": "port", "seconds": best,
+            "sample": f"{wl} generator, first {ns} of {n} genes x {m} samples, one full step "
+                      f"(pickSoftThreshold {len(powers)} powers + adjacency + TOMsimilarity), oracle/restated.py on numpy/BLAS"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from pywgcna_b200.synth import make_expression
+
+    m, n, F, seed, net, tom_type, powers = WORKLOADS[args.workload]
+    ns = min(n, args.cpu_sample_genes)
+    X = make_expression(m, ns, F=F, seed=seed)
+    for _ in range(min(args.warmup, 1)):  # BLAS thread pools warm after one pass; each costs seconds
+        cpu_step(X, net, tom_type, powers)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_step(X, net, tom_type, powers)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = step_flops(m, ns, len(powers)) / dt / 1e12
+    sample = (f"{args.workload} generator, first {ns} of {n} genes x {m} samples per step, reference algorithm "
+              f"(oracle/restated.py port; the Python reference tree does not travel to the GPU box)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "genes": n, "samples": m, "powers": len(powers),
+                   "networkType": net, "TOMType": tom_type, "sample_genes": ns},
+        "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cpu_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import pywgcna_b200 as bw
+    from pywgcna_b200 import _lib as L
+    from pywgcna_b200 import wgcna as W
+    from pywgcna_b200.device import DeviceNetwork
+    from pywgcna_b200.synth import make_expression
+
+    W.VERBOSE = False
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N > 1 with torchrun (python -m torch.distributed.run --nproc-per-node N ...)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = L.load()
+    m, n, F, seed, net, tom_type, powers = WORKLOADS[args.workload]
+    P = len(powers)
+    X_host = torch.from_numpy(make_expression(m, n, F=F, seed=seed)).pin_memory()
+    net_dev = DeviceNetwork(X_host, device=local, networkType=net, precision=args.precision,
+                            world=world, rank=rank)
+    prec_name = {L.PREC_F64: "f64", L.PREC_I8: "i8"}[
+        L.PREC_F64 if lib.b200w_tom_operand_bytes(128, net_dev.prec) == 128 * 128 * 8 else L.PREC_I8]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    tom_events = []
+    state = {}
+
+    def step():
+        flush.zero_()  # L2 flush between steps (256 MiB > 126 MB L2); the big operands exceed L2 anyway
+        net_dev.standardize()
+        k = net_dev.sweep(powers)  # [P, n] on device
+        k_host = k.cpu().numpy()  # D2H of the connectivities (P * n * 8 bytes)
+        pv = np.sort(np.asarray(powers))
+        r2 = np.empty(P)
+        mk = np.empty(P)
+        for i in range(P):
+            r2[i] = W._scale_free_fit(k_host[i], 10)[0]
+            mk[i] = float(W._exact_mean(k_host[i]))
+        ind = (r2 > 0.9) & (mk <= 100)
+        power = int(pv[ind].min()) if ind.any() else int(pv[np.argsort(r2)[-1]])
+        net_dev.adjacency(power)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # events around the contraction only: prepare + exchange happen inside tom() before compute,
+        # so bracket the whole call and subtract nothing -- the contraction dominates; the kernel-only
+        # time comes from the second pair recorded by the library hook below
+        e0.record()
+        T = net_dev.tom(TOMType=tom_type, TOMDenom="min")
+        e1.record()
+        tom_events.append((e0, e1))
+        state["power"] = power
+        state["probe"] = T
+        return power
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    tom_events.clear()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = lib.b200w_launch_count()
+    barrier()
+    t_wall0 = time.time()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    t_wall1 = time.time()
+    launches = lib.b200w_launch_count() - launches0
+    ms_total = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    tom_ms = float(np.mean([a.elapsed_time(b) for a, b in tom_events]))
+
+    # dominant kernel alone (the A.A contraction + TOM epilogue): CUDA events on the launching stream
+    op = net_dev._operand()
+    st = torch.cuda.current_stream().cuda_stream
+    A_rows = net_dev.A[:net_dev.nrows]
+    kern_ms = []
+    tt, td = L.TOM_TYPES.index(tom_type), 0
+    for i in range(2 + min(args.steps, 5)):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(lib.b200w_dev_tom_compute(A_rows.data_ptr(), op.data_ptr(), net_dev.op_rows,
+                                          net_dev._scale.data_ptr(), net_dev._k.data_ptr(), n, net_dev.row0,
+                                          net_dev.nrows, tt, td, L.OUT_TOM, net_dev.prec, net_dev.T.data_ptr(),
+                                          local, st))
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            kern_ms.append(e0.elapsed_time(e1))
+    kern = float(np.mean(kern_ms))
+    kern_flops = 2.0 * net_dev.nrows * n * n  # this rank's share of 2 n^3
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    bf16 = peaks.get("bf16_tflops", 1590.0)
+    peak_src = "measured bf16 burst (MEASURED_PEAKS.json)" if "bf16_tflops" in peaks else "fallback 1590"
+    if prec_name == "i8":
+        mmas = int(os.environ.get("B200W_I8_PAIRS", "15"))
+        peak = 2.0 * bf16 / mmas
+        peak_note = (f"kind::i8 peak taken as 2 x {peak_src} = {2 * bf16:.0f} TOP/s (not separately measured) "
+                     f"/ {mmas} slice-pair MMAs per logical product")
+    else:
+        peak = 37.0
+        peak_note = "FP64 DMMA nominal 37 TFLOP/s (HGX B200 spec; MEASURED_PEAKS.json has no f64 figure)"
+    roofline = {"bound": "tensor", "achieved": kern_flops / kern / 1e9, "peak": peak, "unit": "TFLOP/s",
+                "frac": kern_flops / kern / 1e9 / peak, "traffic": None, "kernel": f"tom_compute[{prec_name}]",
+                "kernel_ms": kern, "share_of_step": kern / ms_step, "peak_note": peak_note}
+
+    # end to end through the public drop-in API (host buffers in, host buffers out)
+    e2e = None
+    if not args.no_e2e and rank == 0 and world == 1:
+        import pandas as pd
+
+        df = pd.DataFrame(X_host.numpy())
+        ksteps = max(1, min(args.steps, 3))
+
+        def e2e_step():
+            p, _ = bw.pickSoftThreshold(df, networkType=net, powerVector=powers, device=local)
+            A = bw.adjacency(df, adjacencyType=net, power=p, device=local)
+            T = bw.TOMsimilarity(A, TOMType=tom_type, device=local, precision=args.precision)
+            return T
+
+        e2e_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            T = e2e_step()
+        dt = (time.perf_counter() - t0) / ksteps
+        e2e = {"value": step_flops(m, n, P) / dt / 1e12, "unit": "TFLOP/s", "seconds": dt, "steps": ksteps,
+               "h2d_bytes_per_step": 2 * m * n * 8 + n * n * 8,
+               "d2h_bytes_per_step": P * n * 8 + n + 2 * n * n * 8,
+               "api": "pickSoftThreshold + adjacency + TOMsimilarity (pandas/numpy in, numpy/pandas out)"}
+        del T
+    cpu = None
+    if not args.no_cpu_baseline and rank == 0 and world == 1:
+        cpu = cpu_baseline(args.workload, args.cpu_sample_genes)
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": step_flops(m, n, P) / ms_step / 1e9, "unit": "TFLOP/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "seconds": ms_step / 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": prec_name if prec_name == "f64" else "s8 digits -> s32 (f64-grade fixed point) + f64",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "genes": n, "samples": m, "powers": P, "networkType": net,
+                       "TOMType": tom_type, "TOMDenom": "min", "selected_power": state["power"],
+                       "tom_precision": prec_name, "l2": "256 MiB flush each step; operands (3.2 GB+) exceed L2",
+                       "parallelism": f"row-block x{world}"},
+            "clocks": clocks, "gpu_launches": int(launches), "tom_ms_in_step": tom_ms,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -144,11 +144,15 @@ int b200w_dev_check_adjacency(const double* dA, int64_t n, double* d_stats4, int
 int64_t b200w_padded_n(int64_t n);
 /* bytes of the full operand buffer for n genes at the given precision */
 int64_t b200w_tom_operand_bytes(int64_t n, int precision);
+/* op_rows = rows allocated per operand plane, >= round_up(n, 128) and a multiple of 128 (a
+ * multi-GPU caller pads it to world * rows_per_rank so that equal blocks can be all-gathered);
+ * rows >= n must be zero (allocate the buffer zeroed).  d_scale and d_k hold op_rows doubles. */
 int b200w_dev_tom_prepare(const double* dA_rows /* nrows x n */, int64_t n, int64_t row0,
-                          int64_t nrows, int precision, void* d_operand, double* d_scale /* n */,
-                          double* d_k /* n */, int device, void* stream);
+                          int64_t nrows, int precision, void* d_operand, int64_t op_rows,
+                          double* d_scale, double* d_k, int device, void* stream);
 int b200w_dev_tom_compute(const double* dA_rows /* nrows x n, original */, const void* d_operand,
-                          const double* d_scale, const double* d_k, int64_t n, int64_t row0,
+                          int64_t op_rows, const double* d_scale, const double* d_k, int64_t n,
+                          int64_t row0,
                           int64_t nrows, int tom_type, int tom_denom, int out_mode, int precision,
                           double* d_out /* nrows x n */, int device, void* stream);
 

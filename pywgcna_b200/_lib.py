@@ -53,8 +53,8 @@ SIGNATURES = {
     "b200w_dev_check_adjacency": (_int, [_dp, _i64, _dp, _int, _dp]),
     "b200w_padded_n": (_i64, [_i64]),
     "b200w_tom_operand_bytes": (_i64, [_i64, _int]),
-    "b200w_dev_tom_prepare": (_int, [_dp, _i64, _i64, _i64, _int, _dp, _dp, _dp, _int, _dp]),
-    "b200w_dev_tom_compute": (_int, [_dp, _dp, _dp, _dp, _i64, _i64, _i64, _int, _int, _int, _int,
+    "b200w_dev_tom_prepare": (_int, [_dp, _i64, _i64, _i64, _int, _dp, _i64, _dp, _dp, _int, _dp]),
+    "b200w_dev_tom_compute": (_int, [_dp, _dp, _i64, _dp, _dp, _i64, _i64, _i64, _int, _int, _int, _int,
                                      _dp, _int, _dp]),
     "b200w_launch_count": (_i64, []),
     "b200w_last_kernel_ms": (_dbl, []),

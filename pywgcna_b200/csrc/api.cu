@@ -177,14 +177,16 @@ static int tom_from_device_adjacency(const double* dA, int64_t n, int tom_type, 
   DevBuf dOp, dScale, dK, dOut;
   precision = resolve_precision(precision);
   B200W_CUDA(dOp.alloc((size_t)b200w_tom_operand_bytes(n, precision)));
-  B200W_CUDA(dScale.alloc((size_t)n * 8));
-  B200W_CUDA(dK.alloc((size_t)n * 8));
+  B200W_CUDA(dScale.alloc((size_t)round_up(n, 128) * 8));
+  B200W_CUDA(dK.alloc((size_t)round_up(n, 128) * 8));
+  B200W_CUDA(cudaMemsetAsync(dOp.p, 0, (size_t)b200w_tom_operand_bytes(n, precision), s));
   B200W_CUDA(dOut.alloc((size_t)nrows * n * 8));
-  if (int e = b200w_dev_tom_prepare(dA, n, 0, n, precision, dOp.p, dScale.as<double>(),
+  const int64_t op_rows = round_up(n, 128);
+  if (int e = b200w_dev_tom_prepare(dA, n, 0, n, precision, dOp.p, op_rows, dScale.as<double>(),
                                     dK.as<double>(), device, s))
     return e;
-  if (int e = b200w_dev_tom_compute(dA + row0 * n, dOp.p, dScale.as<double>(), dK.as<double>(), n,
-                                    row0, nrows, tom_type, tom_denom, out_mode, precision,
+  if (int e = b200w_dev_tom_compute(dA + row0 * n, dOp.p, op_rows, dScale.as<double>(),
+                                    dK.as<double>(), n, row0, nrows, tom_type, tom_denom, out_mode, precision,
                                     dOut.as<double>(), device, s))
     return e;
   B200W_CUDA(cudaMemcpyAsync(out_host, dOut.p, (size_t)nrows * n * 8, cudaMemcpyDeviceToHost, s));

@@ -181,7 +181,7 @@ extern "C" int64_t b200w_tom_operand_bytes(int64_t n, int precision) {
   // rows are padded to a whole number of 128-row operand tiles as well, so that TMA boxes of the
   // int8 path never start outside the tensor
   const int64_t rows = round_up(n, 128);
-  if (precision == B200W_PREC_F64) return rows * ldn * 8;
+  if (resolve_precision(precision) == B200W_PREC_F64) return rows * ldn * 8;
   return (int64_t)B200W_I8_SLICES * rows * ldn;
 }
 
@@ -202,8 +202,10 @@ extern "C" int b200w_dev_check_adjacency(const double* dA, int64_t n, double* d_
 }
 
 int b200w_tom_prepare_i8(const double* dA_rows, int64_t n, int64_t row0, int64_t nrows,
-                         void* d_operand, double* d_scale, double* d_k, cudaStream_t st);
-int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, const double* d_scale,
+                         void* d_operand, int64_t op_rows, double* d_scale, double* d_k,
+                         cudaStream_t st);
+int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t op_rows,
+                         const double* d_scale,
                          const double* d_k, int64_t n, int64_t row0, int64_t nrows, int tom_type,
                          int tom_denom, int out_mode, double* d_out, cudaStream_t st);
 
@@ -213,10 +215,12 @@ int b200w::resolve_precision(int precision) {
 }
 
 extern "C" int b200w_dev_tom_prepare(const double* dA_rows, int64_t n, int64_t row0, int64_t nrows,
-                                     int precision, void* d_operand, double* d_scale, double* d_k,
-                                     int device, void* stream) {
+                                     int precision, void* d_operand, int64_t op_rows,
+                                     double* d_scale, double* d_k, int device, void* stream) {
   if (!dA_rows || !d_operand || !d_k || n < 1 || row0 < 0 || nrows < 1 || row0 + nrows > n)
     return fail(B200W_E_INVALID, "tom_prepare: bad args");
+  if (op_rows < round_up(n, 128) || op_rows % 128)
+    return fail(B200W_E_INVALID, "tom_prepare: op_rows must be a multiple of 128 >= n");
   precision = resolve_precision(precision);
   if (int e = ensure_device(device)) return e;
   cudaStream_t st = (cudaStream_t)stream;
@@ -228,19 +232,22 @@ extern "C" int b200w_dev_tom_prepare(const double* dA_rows, int64_t n, int64_t r
   }
   if (precision == B200W_PREC_I8) {
     if (!d_scale) return fail(B200W_E_INVALID, "tom_prepare: i8 needs d_scale");
-    return b200w_tom_prepare_i8(dA_rows, n, row0, nrows, d_operand, d_scale, d_k, st);
+    return b200w_tom_prepare_i8(dA_rows, n, row0, nrows, d_operand, op_rows, d_scale, d_k, st);
   }
   return fail(B200W_E_INVALID, "tom_prepare: unknown precision %d", precision);
 }
 
 extern "C" int b200w_dev_tom_compute(const double* dA_rows, const void* d_operand,
-                                     const double* d_scale, const double* d_k, int64_t n,
+                                     int64_t op_rows, const double* d_scale, const double* d_k,
+                                     int64_t n,
                                      int64_t row0, int64_t nrows, int tom_type, int tom_denom,
                                      int out_mode, int precision, double* d_out, int device,
                                      void* stream) {
   if (!dA_rows || !d_operand || !d_k || !d_out || n < 1 || row0 < 0 || nrows < 1 ||
       row0 + nrows > n)
     return fail(B200W_E_INVALID, "tom_compute: bad args");
+  if (op_rows < round_up(n, 128) || op_rows % 128)
+    return fail(B200W_E_INVALID, "tom_compute: op_rows must be a multiple of 128 >= n");
   if (tom_type < 0 || tom_type > 1 || tom_denom < 0 || tom_denom > 1 || out_mode < 0 || out_mode > 2)
     return fail(B200W_E_INVALID, "tom_compute: bad enum");
   precision = resolve_precision(precision);
@@ -259,7 +266,7 @@ extern "C" int b200w_dev_tom_compute(const double* dA_rows, const void* d_operan
   }
   if (precision == B200W_PREC_I8) {
     if (!d_scale) return fail(B200W_E_INVALID, "tom_compute: i8 needs d_scale");
-    return b200w_tom_compute_i8(dA_rows, d_operand, d_scale, d_k, n, row0, nrows, tom_type,
+    return b200w_tom_compute_i8(dA_rows, d_operand, op_rows, d_scale, d_k, n, row0, nrows, tom_type,
                                 tom_denom, out_mode, d_out, st);
   }
   return fail(B200W_E_INVALID, "tom_compute: unknown precision %d", precision);

