@@ -1,9 +1,523 @@
-// placeholder: the tcgen05 int8-slice contraction lands here
-#include "common.cuh"
-using namespace b200w;
-int b200w_tom_prepare_i8(const double*, int64_t, int64_t, int64_t, void*, int64_t, double*, double*, cudaStream_t) {
-  return fail(B200W_E_UNSUPPORTED, "i8 TOM path not built yet");
+// K4, tensor-core flavour: L = A.A on tcgen05 (kind::i8, s8 x s8 -> s32 in TMEM) fed by TMA, with the
+// TOM epilogue fused.  Replaces np `A @ A` + the elementwise tail of TomSimilarityFromAdj
+// (PyWGCNA/wgcna.py:1145-1156).
+//
+// Arithmetic ("digit slices", an Ozaki-style split made for int8 tensor cores).  Every row i of the
+// cleaned adjacency (NaN -> 0, diag -> 0, |a| <= 1) is scaled by a power of two 2^e_i so that its
+// largest magnitude lies in [0.5, 1), rounded to a 38-bit fixed-point integer q_ij and written as S = 5
+// balanced base-256 digits d^s_ij in [-128, 127]  (q = sum_s d^s 256^s).  Then
+//     L_ij = sum_u a_iu a_ju = scale_i scale_j  sum_{s,t} 256^(s+t)  sum_u d^s_iu d^t_ju ,   scale = 2^-(e+38)
+// where each inner sum is an s8 x s8 GEMM accumulated EXACTLY in int32 (A is symmetric to 1e-12 --
+// checkAdjMat -- so the same digit planes serve as both operands, K-major).  Digit pairs are grouped
+// by weight w = s + t; pairs with w < w_min (their total is below 2^-40 of the leading term per product)
+// are dropped.  A "pass" accumulates pairs of one weight into one TMEM accumulator for at most 1023
+// K-blocks of 128 (|sum| <= 1023 * 128 * 2^14 < 2^31: no overflow for ANY input), then the epilogue
+// warps add acc * 256^(w - w_min) to a float64 running sum.  Integer accumulation has no rounding, so
+// the result does not depend on the order of K-blocks, on the tile schedule or on the number of GPUs.
+//
+// Kernel structure (persistent, one CTA per SM, 256 threads):
+//   warp 0   TMA producer: 4-stage ring of {A tile 128 x 128 B, B tile 256 x 128 B}, SWIZZLE_128B
+//   warp 1   MMA issuer: one lane issues tcgen05.mma M128 N256 K32, 4 per stage; tcgen05.commit frees
+//            the stage and, at the end of a pass, publishes the accumulator
+//   warp 2   TMEM allocator (512 columns = two 128 x 256 s32 accumulators, double buffered)
+//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns, float64 running sum in an L2-resident per-CTA
+//            scratch (coalesced: lanes = rows), last pass applies (L + a) / (min(k_i,k_j) + 1 - a)
+#include <cuda.h>
+
+#include <vector>
+
+#include "tom_common.cuh"
+
+namespace b200w {
+
+constexpr int kS = B200W_I8_SLICES;  // digit planes stored
+constexpr int kFixBits = 8 * kS - 2;  // 38
+constexpr int kTM = 128, kTN = 256, kKB = 128;  // tile rows, tile cols, K bytes per stage
+constexpr int kI8Stages = 4;
+constexpr int kStageBytes = (kTM + kTN) * kKB;  // 48 KB
+constexpr int kMaxSegs = 96, kMaxPasses = 48;
+constexpr int kI8Threads = 256;
+constexpr int kMaxKbPerPass = 1023;
+
+struct Seg {
+  int16_t s, t;    // digit planes of the left (row) and right (column) operand
+  int32_t kb0, kb1;  // K-block range [kb0, kb1)
+  int32_t pass;    // pass index this segment belongs to
+};
+
+struct I8Params {
+  const double* A_rows;  // nrows x n original adjacency rows (for a_ij)
+  const double* scale;   // op_rows
+  const double* k;       // op_rows
+  double* out;           // nrows x n
+  double* scratch;       // gridDim.x * 128 * 256
+  int64_t n, row0, nrows;
+  int32_t tiles_m, tiles_n;
+  int32_t nseg, npass;
+  int32_t tom_type, tom_denom, out_mode;
+  double final_scale;    // 256^w_min
+  Seg seg[kMaxSegs];
+  double pass_w[kMaxPasses];  // 256^(w - w_min)
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
 }
-int b200w_tom_compute_i8(const double*, const void*, int64_t, const double*, const double*, int64_t, int64_t, int64_t, int, int, int, double*, cudaStream_t) {
-  return fail(B200W_E_UNSUPPORTED, "i8 TOM path not built yet");
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded spin: a protocol bug must end as a trapped launch, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                            int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"
+      "%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address
+// [0,14) >> 4, LBO [16,30) (unused for swizzled K-major, 1), SBO [32,46) = 8 rows * 128 B = 1024 B,
+// version [46,48) = 1, layout type [61,64) = 2 (SWIZZLE_128B).  Tiles are 1024-byte aligned.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format [4,6) = 2 (S32), a_format [7,10) = 1
+// (signed int8), b_format [10,13) = 1, a/b major = K (0), n_dim [17,23) = N >> 3, m_dim [24,29) = M >> 4.
+__host__ __device__ constexpr uint32_t make_i8_idesc(int M, int N) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Operand preparation: one CTA per row.  rmax -> e_i, 38-bit fixed point, 5 balanced digits per entry
+// written to the 5 planes (rows zero padded to ldn); k_i = sum_j a_ij (wgcna.py:1146); scale_i.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tom_prepare_i8_kernel(const double* __restrict__ A_rows, int64_t n, int64_t ldn, int64_t op_rows,
+                      int64_t row0, int8_t* __restrict__ planes, double* __restrict__ scale,
+                      double* __restrict__ k) {
+  __shared__ double red[8];
+  const int64_t i = row0 + blockIdx.x;
+  const double* src = A_rows + (int64_t)blockIdx.x * n;
+  double s = 0.0, mx = 0.0;
+  for (int64_t j = threadIdx.x; j < n; j += 256) {
+    double a = tom_clean(src[j], i, j);
+    s += a;
+    mx = fmax(mx, fabs(a));
+  }
+  s = block_sum_256(s);
+  for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmax(mx, red[w]);
+  int ex = 0;
+  if (mx > 0.0) frexp(mx, &ex);  // mx = f * 2^ex, f in [0.5, 1)  ->  mx * 2^-ex in [0.5, 1)
+  if (ex < -900) ex = -900;      // keeps 2^(38 - ex) finite; such rows contribute < 1e-270 anyway
+  // up = 2^(kFixBits - ex): a * up is exact (power of two) and |a * up| <= 2^38
+  const double up = ldexp(1.0, kFixBits - ex);
+  if (threadIdx.x == 0) {
+    k[i] = s;
+    scale[i] = ldexp(1.0, ex - kFixBits);
+  }
+  const int64_t plane_stride = op_rows * ldn;
+  int8_t* dst = planes + i * ldn;
+  for (int64_t j4 = (int64_t)threadIdx.x * 4; j4 < ldn; j4 += 256 * 4) {
+    uint32_t packed[kS];
+#pragma unroll
+    for (int p = 0; p < kS; ++p) packed[p] = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int64_t j = j4 + e;
+      long long q = 0;
+      if (j < n) q = __double2ll_rn(tom_clean(src[j], i, j) * up);
+#pragma unroll
+      for (int p = 0; p < kS; ++p) {
+        long long d = ((q + 128) & 255) - 128;  // balanced digit in [-128, 127]
+        q = (q - d) >> 8;
+        packed[p] |= ((uint32_t)(d & 255)) << (8 * e);
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < kS; ++p)
+      *reinterpret_cast<uint32_t*>(dst + p * plane_stride + j4) = packed[p];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The contraction kernel
+// ---------------------------------------------------------------------------------------------
+struct __align__(8) I8Barriers {
+  uint64_t full[kI8Stages], empty[kI8Stages], tmem_full[2], tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void i8_tile_coords(const I8Params& p, int64_t tile, int64_t& tm, int64_t& tn) {
+  grouped_tile(tile, p.tiles_m, p.tiles_n, 16, tm, tn);
+}
+
+__global__ void __launch_bounds__(kI8Threads, 1)
+tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ I8Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  I8Barriers* bars = reinterpret_cast<I8Barriers*>(smem + kI8Stages * kStageBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_tiles = (int64_t)p.tiles_m * p.tiles_n;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kI8Stages; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&bars->tmem_full[a], 1);
+      mbar_init(&bars->tmem_empty[a], 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int64_t tm, tn;
+        i8_tile_coords(p, tile, tm, tn);
+        const int i0 = (int)(p.row0 + tm * kTM), j0 = (int)(tn * kTN);
+        for (int sg = 0; sg < p.nseg; ++sg) {
+          const Seg sgm = p.seg[sg];
+          for (int kb = sgm.kb0; kb < sgm.kb1; ++kb) {
+            mbar_wait(&bars->empty[stage], phase ^ 1);
+            uint8_t* a_dst = smem + stage * kStageBytes;
+            uint8_t* b_dst = a_dst + kTM * kKB;
+            mbar_expect_tx(&bars->full[stage], kStageBytes);
+            tma_load_3d(a_dst, &tmap, &bars->full[stage], kb * kKB, i0, sgm.s);
+            tma_load_3d(b_dst, &tmap, &bars->full[stage], kb * kKB, j0, sgm.t);
+            tma_load_3d(b_dst + 128 * kKB, &tmap, &bars->full[stage], kb * kKB, j0 + 128, sgm.t);
+            if (++stage == kI8Stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ====================================== MMA issuer ======================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_i8_idesc(kTM, kTN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int cur_pass = -1;
+        bool first = true;
+        for (int sg = 0; sg < p.nseg; ++sg) {
+          const Seg sgm = p.seg[sg];
+          if (sgm.pass != cur_pass) {  // a new pass starts: wait until the epilogue has drained this accumulator
+            cur_pass = sgm.pass;
+            mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            first = true;
+          }
+          const uint32_t tmem_d = tmem_base + (uint32_t)acc * kTN;
+          for (int kb = sgm.kb0; kb < sgm.kb1; ++kb) {
+            mbar_wait(&bars->full[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
+            const uint64_t adesc = make_sw128_desc(a_addr);
+            const uint64_t bdesc = make_sw128_desc(a_addr + kTM * kKB);
+#pragma unroll
+            for (int kk = 0; kk < kKB / 32; ++kk) {
+              // K advance inside the 128-byte swizzle atom: +32 bytes on the start address (>> 4 = 2)
+              tc_mma_i8(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, first ? 0u : 1u);
+              first = false;
+            }
+            tc_commit(&bars->empty[stage]);  // frees the smem stage when these MMAs retire
+            if (++stage == kI8Stages) { stage = 0; phase ^= 1; }
+          }
+          const bool pass_ends = (sg + 1 == p.nseg) || (p.seg[sg + 1].pass != cur_pass);
+          if (pass_ends) {
+            tc_commit(&bars->tmem_full[acc]);  // accumulator complete -> epilogue
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ======================================= epilogue =======================================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    double* scratch = p.scratch + (int64_t)blockIdx.x * (kTM * kTN);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      int64_t tm, tn;
+      i8_tile_coords(p, tile, tm, tn);
+      const int64_t gi = p.row0 + tm * kTM + row, j0 = tn * kTN;
+      const bool row_ok = gi < p.row0 + p.nrows;
+      const double ki = row_ok ? p.k[gi] : 0.0;
+      const double si = row_ok ? p.scale[gi] * p.final_scale : 0.0;
+      const double* arow = p.A_rows + (row_ok ? (gi - p.row0) : 0) * p.n;
+      double* orow = p.out + (row_ok ? (gi - p.row0) : 0) * p.n;
+      for (int ps = 0; ps < p.npass; ++ps) {
+        mbar_wait(&bars->tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const double w = p.pass_w[ps];
+        const bool first = ps == 0, last = ps + 1 == p.npass;
+#pragma unroll 1
+        for (int c = 0; c < kTN / 32; ++c) {
+          uint32_t r[32];
+          tc_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTN + c * 32), r);
+          double* sc = scratch + (int64_t)c * 32 * kTM + row;  // [c][col][row]: lanes = consecutive rows
+          if (!last) {
+#pragma unroll
+            for (int col = 0; col < 32; ++col) {
+              double v = (double)(int)r[col] * w;
+              if (!first) v += sc[col * kTM];
+              sc[col * kTM] = v;
+            }
+          } else {
+#pragma unroll
+            for (int col = 0; col < 32; ++col) {
+              double v = (double)(int)r[col] * w;
+              if (!first) v += sc[col * kTM];
+              const int64_t gj = j0 + c * 32 + col;
+              if (row_ok && gj < p.n) {
+                const double L = v * (si * p.scale[gj]);
+                const double a = tom_clean(arow[gj], gi, gj);
+                orow[gj] = tom_value(L, a, ki, p.k[gj], gi == gj, p.tom_type, p.tom_denom, p.out_mode);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = (EncodeTiledFn)sym;
+  return fn;
+}
+
+// Digit-pair schedule: pairs (s, t) with s + t >= w_min, grouped by weight (heaviest first), cut into
+// passes of at most kMaxKbPerPass K-blocks.
+static int build_schedule(I8Params& prm, int nkb, int w_min) {
+  int nseg = 0, npass = 0;
+  for (int w = 2 * (kS - 1); w >= w_min; --w) {
+    int in_pass = 0;
+    bool open = false;
+    for (int s = kS - 1; s >= 0; --s) {
+      int t = w - s;
+      if (t < 0 || t >= kS) continue;
+      int kb = 0;
+      while (kb < nkb) {
+        if (!open || in_pass == kMaxKbPerPass) {
+          if (npass == kMaxPasses) return -1;
+          prm.pass_w[npass] = ldexp(1.0, 8 * (w - w_min));
+          ++npass;
+          in_pass = 0;
+          open = true;
+        }
+        int take = nkb - kb;
+        if (take > kMaxKbPerPass - in_pass) take = kMaxKbPerPass - in_pass;
+        if (nseg == kMaxSegs) return -1;
+        prm.seg[nseg].s = (int16_t)s;
+        prm.seg[nseg].t = (int16_t)t;
+        prm.seg[nseg].kb0 = kb;
+        prm.seg[nseg].kb1 = kb + take;
+        prm.seg[nseg].pass = npass - 1;
+        ++nseg;
+        kb += take;
+        in_pass += take;
+      }
+    }
+  }
+  prm.nseg = nseg;
+  prm.npass = npass;
+  prm.final_scale = ldexp(1.0, 8 * w_min);
+  return 0;
+}
+
+}  // namespace b200w
+
+using namespace b200w;
+
+int b200w_tom_prepare_i8(const double* dA_rows, int64_t n, int64_t row0, int64_t nrows, void* d_operand,
+                         int64_t op_rows, double* d_scale, double* d_k, cudaStream_t st) {
+  const int64_t ldn = b200w_padded_n(n);
+  tom_prepare_i8_kernel<<<(unsigned)nrows, 256, 0, st>>>(dA_rows, n, ldn, op_rows, row0, (int8_t*)d_operand,
+                                                         d_scale, d_k);
+  B200W_LAUNCHED();
+  return 0;
+}
+
+int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t op_rows, const double* d_scale,
+                         const double* d_k, int64_t n, int64_t row0, int64_t nrows, int tom_type, int tom_denom,
+                         int out_mode, double* d_out, cudaStream_t st) {
+  const int64_t ldn = b200w_padded_n(n);
+  if (op_rows > 0x7fffffff || ldn > 0x7fffffff) return fail(B200W_E_UNSUPPORTED, "tom_i8: n too large");
+  EncodeTiledFn encode = get_encode_tiled();
+  if (!encode) return fail(B200W_E_CUDA, "tom_i8: cuTensorMapEncodeTiled not available from the driver");
+
+  CUtensorMap tmap;
+  const cuuint64_t gdim[3] = {(cuuint64_t)ldn, (cuuint64_t)op_rows, (cuuint64_t)kS};
+  const cuuint64_t gstride[2] = {(cuuint64_t)ldn, (cuuint64_t)ldn * (cuuint64_t)op_rows};  // bytes, dims 1..2
+  const cuuint32_t box[3] = {(cuuint32_t)kKB, 128u, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(d_operand), gdim, gstride, box,
+                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return fail(B200W_E_CUDA, "tom_i8: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+
+  static I8Params prm;  // large (schedule tables); filled per call under the caller's single-thread contract
+  prm.A_rows = dA_rows;
+  prm.scale = d_scale;
+  prm.k = d_k;
+  prm.out = d_out;
+  prm.n = n;
+  prm.row0 = row0;
+  prm.nrows = nrows;
+  prm.tiles_m = (int32_t)((nrows + kTM - 1) / kTM);
+  prm.tiles_n = (int32_t)((n + kTN - 1) / kTN);
+  prm.tom_type = tom_type;
+  prm.tom_denom = tom_denom;
+  prm.out_mode = out_mode;
+  int w_min = kS - 1;
+  if (const char* e = getenv("B200W_I8_WMIN")) w_min = atoi(e);
+  if (w_min < 0 || w_min > 2 * (kS - 1)) return fail(B200W_E_INVALID, "tom_i8: bad B200W_I8_WMIN");
+  if (build_schedule(prm, (int)(ldn / kKB), w_min))
+    return fail(B200W_E_UNSUPPORTED, "tom_i8: schedule too long for n = %lld", (long long)n);
+
+  int dev = 0, sms = 0;
+  B200W_CUDA(cudaGetDevice(&dev));
+  B200W_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t n_tiles = (int64_t)prm.tiles_m * prm.tiles_n;
+  const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+  Scratch scratch;
+  B200W_CUDA(scratch.alloc((size_t)grid * kTM * kTN * sizeof(double), st));
+  prm.scratch = scratch.as<double>();
+
+  const size_t smem = (size_t)kI8Stages * kStageBytes + sizeof(I8Barriers) + 1024;
+  B200W_CUDA(cudaFuncSetAttribute(tom_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool timed = getenv("B200W_TIME_KERNELS") != nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (timed) {
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+  }
+  tom_i8_kernel<<<grid, kI8Threads, smem, st>>>(tmap, prm);
+  B200W_LAUNCHED();
+  if (timed) {
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    g_last_kernel_ms = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
+  return 0;
 }
