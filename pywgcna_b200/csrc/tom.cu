@@ -210,7 +210,7 @@ int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t o
                          int tom_denom, int out_mode, double* d_out, cudaStream_t st);
 
 int b200w::resolve_precision(int precision) {
-  if (precision == B200W_PREC_AUTO) return B200W_PREC_F64;  // TODO(i8): flip once tom_i8 is parity-green
+  if (precision == B200W_PREC_AUTO) return B200W_PREC_I8;
   return precision;
 }
 

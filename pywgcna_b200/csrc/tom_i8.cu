@@ -54,7 +54,9 @@ struct I8Params {
   int64_t n, row0, nrows;
   int32_t tiles_m, tiles_n;
   int32_t nseg, npass;
-  int32_t tom_type, tom_denom, out_mode;
+  int32_t tom_type, tom_denom, out_mode, group;
+  int32_t sync_mode;       // 0 none, 1 grid barrier of the producers per tile, 2 per segment
+  unsigned int* sync_ctr;  // zeroed before launch
   double final_scale;    // 256^w_min
   Seg seg[kMaxSegs];
   double pass_w[kMaxPasses];  // 256^(w - w_min)
@@ -214,7 +216,7 @@ struct __align__(8) I8Barriers {
 };
 
 __device__ __forceinline__ void i8_tile_coords(const I8Params& p, int64_t tile, int64_t& tm, int64_t& tn) {
-  grouped_tile(tile, p.tiles_m, p.tiles_n, 16, tm, tn);
+  grouped_tile(tile, p.tiles_m, p.tiles_n, p.group, tm, tn);
 }
 
 __global__ void __launch_bounds__(kI8Threads, 1)
@@ -254,12 +256,32 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        int64_t tm, tn;
-        i8_tile_coords(p, tile, tm, tn);
+      // Every CTA runs the same number of iterations so that the producers can keep in step: CTAs
+      // that stream the same operand panels must do so within the L2 residency time, or each of them
+      // fetches the panel from HBM again (measured: 525 GB of DRAM reads per launch without the
+      // barrier against ~110 GB of unique panel bytes).
+      const int64_t iters = (n_tiles + gridDim.x - 1) / gridDim.x;
+      unsigned int sync_seq = 0;
+      for (int64_t it = 0; it < iters; ++it) {
+        const int64_t tile = blockIdx.x + it * gridDim.x;
+        const bool active = tile < n_tiles;
+        int64_t tm = 0, tn = 0;
+        if (active) i8_tile_coords(p, tile, tm, tn);
         const int i0 = (int)(p.row0 + tm * kTM), j0 = (int)(tn * kTN);
         for (int sg = 0; sg < p.nseg; ++sg) {
           const Seg sgm = p.seg[sg];
+          if (p.sync_mode == 2 || (p.sync_mode == 1 && sg == 0)) {
+            ++sync_seq;
+            __threadfence();
+            atomicAdd(p.sync_ctr, 1u);
+            const unsigned int target = sync_seq * gridDim.x;
+            unsigned int v, spins = 0;
+            do {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.sync_ctr) : "memory");
+              if (++spins > (1u << 24)) __trap();
+            } while (v < target);
+          }
+          if (!active) continue;
           for (int kb = sgm.kb0; kb < sgm.kb1; ++kb) {
             mbar_wait(&bars->empty[stage], phase ^ 1);
             uint8_t* a_dst = smem + stage * kStageBytes;
@@ -484,6 +506,8 @@ int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t o
   prm.tom_type = tom_type;
   prm.tom_denom = tom_denom;
   prm.out_mode = out_mode;
+  prm.group = 16;
+  if (const char* e = getenv("B200W_I8_GROUP")) prm.group = atoi(e) > 0 ? atoi(e) : 16;
   int w_min = kS - 1;
   if (const char* e = getenv("B200W_I8_WMIN")) w_min = atoi(e);
   if (w_min < 0 || w_min > 2 * (kS - 1)) return fail(B200W_E_INVALID, "tom_i8: bad B200W_I8_WMIN");
@@ -508,7 +532,26 @@ int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t o
     cudaEventCreate(&e1);
     cudaEventRecord(e0, st);
   }
-  tom_i8_kernel<<<grid, kI8Threads, smem, st>>>(tmap, prm);
+  prm.sync_mode = 1;
+  if (const char* e = getenv("B200W_I8_SYNC")) prm.sync_mode = atoi(e);
+  Scratch ctr;
+  B200W_CUDA(ctr.alloc(64, st));
+  B200W_CUDA(cudaMemsetAsync(ctr.p, 0, 64, st));
+  prm.sync_ctr = ctr.as<unsigned int>();
+  {
+    // cooperative launch: all CTAs are guaranteed co-resident, which the producer barrier needs
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kI8Threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B200W_CUDA(cudaLaunchKernelEx(&cfg, tom_i8_kernel, tmap, prm));
+  }
   B200W_LAUNCHED();
   if (timed) {
     cudaEventRecord(e1, st);
