@@ -33,8 +33,6 @@ namespace b200w {
 constexpr int kS = B200W_I8_SLICES;  // digit planes stored
 constexpr int kFixBits = 8 * kS - 2;  // 38
 constexpr int kTM = 128, kTN = 256, kKB = 128;  // tile rows, tile cols, K bytes per stage
-constexpr int kI8Stages = 4;
-constexpr int kStageBytes = (kTM + kTN) * kKB;  // 48 KB
 constexpr int kMaxSegs = 96, kMaxPasses = 48;
 constexpr int kI8Threads = 256;
 constexpr int kMaxKbPerPass = 1023;
@@ -93,7 +91,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    if (++spins > (1u << 22)) __trap();
   }
 }
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0,
@@ -208,47 +206,115 @@ tom_prepare_i8_kernel(const double* __restrict__ A_rows, int64_t n, int64_t ldn,
 }
 
 // ---------------------------------------------------------------------------------------------
-// The contraction kernel
+// The contraction kernel.  kCtas = 1: one CTA per 128 x 256 tile.  kCtas = 2: a CTA pair (cluster of
+// 2, tcgen05 cta_group::2) per 256 x 256 tile -- each CTA stages its own 128 rows of the row operand
+// and its own 128-row half of the column operand, the leader CTA issues M256 N256 K32 MMAs that
+// read both CTAs' shared memory and write both CTAs' TMEM.  Per SM that is 32 KB of operand per
+// 512 tensor-pipe cycles instead of 48 KB.
 // ---------------------------------------------------------------------------------------------
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // clears the CTA-pair bit of a shared::cluster address
+
+template <int kCtas>
+struct I8Cfg {
+  static constexpr int kBRows = kTN / kCtas;                    // column-operand rows this CTA stages
+  static constexpr int kStageBytes = (kTM + kBRows) * kKB;      // 48 KB / 32 KB
+  static constexpr int kStages = kCtas == 1 ? 4 : 6;            // 192 KB of ring either way
+  static constexpr int kTileRows = kTM * kCtas;                 // output rows per tile (CTA or pair)
+};
+
+template <int kStages>
 struct __align__(8) I8Barriers {
-  uint64_t full[kI8Stages], empty[kI8Stages], tmem_full[2], tmem_empty[2];
+  uint64_t full[kStages], empty[kStages], tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void i8_tile_coords(const I8Params& p, int64_t tile, int64_t& tm, int64_t& tn) {
-  grouped_tile(tile, p.tiles_m, p.tiles_n, p.group, tm, tn);
+template <int kCtas>
+__host__ __device__ constexpr size_t i8_smem_bytes() {
+  return (size_t)I8Cfg<kCtas>::kStages * I8Cfg<kCtas>::kStageBytes + sizeof(I8Barriers<I8Cfg<kCtas>::kStages>) + 1024;
 }
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// remote arrive on the barrier at the same offset in the even CTA of the pair
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerMask) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                                int c1, int c2) {
+  // executed by both CTAs; the transaction bytes are counted on the LEADER's barrier
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int kCtas>
 __global__ void __launch_bounds__(kI8Threads, 1)
 tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ I8Params p) {
+  using Cfg = I8Cfg<kCtas>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int kStageBytes = Cfg::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B tiles need 1024-byte alignment
+  // SWIZZLE_128B tiles need 1024-byte alignment (the dynamic smem base is the same in both CTAs of a
+  // pair, so the aligned offsets match, as cta_group::2 requires)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  I8Barriers* bars = reinterpret_cast<I8Barriers*>(smem + kI8Stages * kStageBytes);
+  auto* bars = reinterpret_cast<I8Barriers<kStages>*>(smem + kStages * kStageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = kCtas == 2 ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int64_t unit = blockIdx.x / kCtas;           // CTA (pair) index
+  const int64_t n_units = gridDim.x / kCtas;
   const int64_t n_tiles = (int64_t)p.tiles_m * p.tiles_n;
 
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kI8Stages; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       mbar_init(&bars->full[s], 1);
       mbar_init(&bars->empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bars->tmem_full[a], 1);
-      mbar_init(&bars->tmem_empty[a], 4);  // one arrive per epilogue warp
+      mbar_init(&bars->tmem_empty[a], 4 * kCtas);  // one arrive per epilogue warp of every CTA
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
-                 "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (kCtas == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                   "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                   "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCtas == 1) __syncthreads(); else cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  const int64_t iters = (n_tiles + n_units - 1) / n_units;
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -260,14 +326,13 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
       // that stream the same operand panels must do so within the L2 residency time, or each of them
       // fetches the panel from HBM again (measured: 525 GB of DRAM reads per launch without the
       // barrier against ~110 GB of unique panel bytes).
-      const int64_t iters = (n_tiles + gridDim.x - 1) / gridDim.x;
       unsigned int sync_seq = 0;
       for (int64_t it = 0; it < iters; ++it) {
-        const int64_t tile = blockIdx.x + it * gridDim.x;
+        const int64_t tile = unit + it * n_units;
         const bool active = tile < n_tiles;
         int64_t tm = 0, tn = 0;
-        if (active) i8_tile_coords(p, tile, tm, tn);
-        const int i0 = (int)(p.row0 + tm * kTM), j0 = (int)(tn * kTN);
+        if (active) grouped_tile(tile, p.tiles_m, p.tiles_n, p.group, tm, tn);
+        const int i0 = (int)(p.row0 + tm * Cfg::kTileRows + rank * kTM), j0 = (int)(tn * kTN);
         for (int sg = 0; sg < p.nseg; ++sg) {
           const Seg sgm = p.seg[sg];
           if (p.sync_mode == 2 || (p.sync_mode == 1 && sg == 0)) {
@@ -286,30 +351,37 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
             mbar_wait(&bars->empty[stage], phase ^ 1);
             uint8_t* a_dst = smem + stage * kStageBytes;
             uint8_t* b_dst = a_dst + kTM * kKB;
-            mbar_expect_tx(&bars->full[stage], kStageBytes);
-            tma_load_3d(a_dst, &tmap, &bars->full[stage], kb * kKB, i0, sgm.s);
-            tma_load_3d(b_dst, &tmap, &bars->full[stage], kb * kKB, j0, sgm.t);
-            tma_load_3d(b_dst + 128 * kKB, &tmap, &bars->full[stage], kb * kKB, j0 + 128, sgm.t);
-            if (++stage == kI8Stages) { stage = 0; phase ^= 1; }
+            if constexpr (kCtas == 1) {
+              mbar_expect_tx(&bars->full[stage], kStageBytes);
+              tma_load_3d(a_dst, &tmap, &bars->full[stage], kb * kKB, i0, sgm.s);
+              tma_load_3d(b_dst, &tmap, &bars->full[stage], kb * kKB, j0, sgm.t);
+              tma_load_3d(b_dst + 128 * kKB, &tmap, &bars->full[stage], kb * kKB, j0 + 128, sgm.t);
+            } else {
+              if (leader) mbar_expect_tx(&bars->full[stage], 2 * kStageBytes);  // both CTAs' bytes
+              tma_load_3d_2sm(a_dst, &tmap, &bars->full[stage], kb * kKB, i0, sgm.s);
+              tma_load_3d_2sm(b_dst, &tmap, &bars->full[stage], kb * kKB, j0 + (int)rank * 128, sgm.t);
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ====================================== MMA issuer ======================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_i8_idesc(kTM, kTN);
+    // ============================ MMA issuer (leader CTA only) ==============================
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_i8_idesc(kTM * kCtas, kTN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int64_t it = 0; it < iters; ++it) {
+        if (unit + it * n_units >= n_tiles) break;
         int cur_pass = -1;
         bool first = true;
         for (int sg = 0; sg < p.nseg; ++sg) {
           const Seg sgm = p.seg[sg];
-          if (sgm.pass != cur_pass) {  // a new pass starts: wait until the epilogue has drained this accumulator
+          if (sgm.pass != cur_pass) {  // a new pass: wait until the epilogue(s) drained this accumulator
             cur_pass = sgm.pass;
             mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
             tc_fence_after();
@@ -325,15 +397,19 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
 #pragma unroll
             for (int kk = 0; kk < kKB / 32; ++kk) {
               // K advance inside the 128-byte swizzle atom: +32 bytes on the start address (>> 4 = 2)
-              tc_mma_i8(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, first ? 0u : 1u);
+              if constexpr (kCtas == 1)
+                tc_mma_i8(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, first ? 0u : 1u);
+              else
+                tc_mma_i8_2sm(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, first ? 0u : 1u);
               first = false;
             }
-            tc_commit(&bars->empty[stage]);  // frees the smem stage when these MMAs retire
-            if (++stage == kI8Stages) { stage = 0; phase ^= 1; }
+            // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+            if constexpr (kCtas == 1) tc_commit(&bars->empty[stage]); else tc_commit_2sm(&bars->empty[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
           const bool pass_ends = (sg + 1 == p.nseg) || (p.seg[sg + 1].pass != cur_pass);
-          if (pass_ends) {
-            tc_commit(&bars->tmem_full[acc]);  // accumulator complete -> epilogue
+          if (pass_ends) {  // accumulator complete -> epilogue warps (of both CTAs)
+            if constexpr (kCtas == 1) tc_commit(&bars->tmem_full[acc]); else tc_commit_2sm(&bars->tmem_full[acc]);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
           }
@@ -348,10 +424,12 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
     double* scratch = p.scratch + (int64_t)blockIdx.x * (kTM * kTN);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int64_t it = 0; it < iters; ++it) {
+      const int64_t tile = unit + it * n_units;
+      if (tile >= n_tiles) break;
       int64_t tm, tn;
-      i8_tile_coords(p, tile, tm, tn);
-      const int64_t gi = p.row0 + tm * kTM + row, j0 = tn * kTN;
+      grouped_tile(tile, p.tiles_m, p.tiles_n, p.group, tm, tn);
+      const int64_t gi = p.row0 + tm * Cfg::kTileRows + rank * kTM + row, j0 = tn * kTN;
       const bool row_ok = gi < p.row0 + p.nrows;
       const double ki = row_ok ? p.k[gi] : 0.0;
       const double si = row_ok ? p.scale[gi] * p.final_scale : 0.0;
@@ -390,17 +468,22 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+        if (lane == 0) {
+          if constexpr (kCtas == 1) mbar_arrive(&bars->tmem_empty[acc]); else mbar_arrive_leader(&bars->tmem_empty[acc]);
+        }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCtas == 1) __syncthreads(); else cluster_sync_all();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if constexpr (kCtas == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -514,17 +597,28 @@ int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t o
   if (build_schedule(prm, (int)(ldn / kKB), w_min))
     return fail(B200W_E_UNSUPPORTED, "tom_i8: schedule too long for n = %lld", (long long)n);
 
+  int ctas = 2;
+  if (const char* e = getenv("B200W_I8_CTAS")) ctas = atoi(e) == 1 ? 1 : 2;
+  prm.tiles_m = (int32_t)((nrows + kTM * ctas - 1) / (kTM * ctas));
   int dev = 0, sms = 0;
   B200W_CUDA(cudaGetDevice(&dev));
   B200W_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int64_t n_tiles = (int64_t)prm.tiles_m * prm.tiles_n;
-  const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+  const int64_t units = n_tiles < sms / ctas ? n_tiles : sms / ctas;
+  const int grid = (int)(units * ctas);
   Scratch scratch;
   B200W_CUDA(scratch.alloc((size_t)grid * kTM * kTN * sizeof(double), st));
   prm.scratch = scratch.as<double>();
+  prm.sync_mode = 2;
+  if (const char* e = getenv("B200W_I8_SYNC")) prm.sync_mode = atoi(e);
+  Scratch ctr;
+  B200W_CUDA(ctr.alloc(64, st));
+  B200W_CUDA(cudaMemsetAsync(ctr.p, 0, 64, st));
+  prm.sync_ctr = ctr.as<unsigned int>();
 
-  const size_t smem = (size_t)kI8Stages * kStageBytes + sizeof(I8Barriers) + 1024;
-  B200W_CUDA(cudaFuncSetAttribute(tom_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = ctas == 1 ? i8_smem_bytes<1>() : i8_smem_bytes<2>();
+  auto kern = ctas == 1 ? tom_i8_kernel<1> : tom_i8_kernel<2>;
+  B200W_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const bool timed = getenv("B200W_TIME_KERNELS") != nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (timed) {
@@ -532,25 +626,32 @@ int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t o
     cudaEventCreate(&e1);
     cudaEventRecord(e0, st);
   }
-  prm.sync_mode = 1;
-  if (const char* e = getenv("B200W_I8_SYNC")) prm.sync_mode = atoi(e);
-  Scratch ctr;
-  B200W_CUDA(ctr.alloc(64, st));
-  B200W_CUDA(cudaMemsetAsync(ctr.p, 0, 64, st));
-  prm.sync_ctr = ctr.as<unsigned int>();
   {
-    // cooperative launch: all CTAs are guaranteed co-resident, which the producer barrier needs
+    // cooperative launch: every CTA is guaranteed co-resident, which the producer barrier needs
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(kI8Threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeCooperative;
-    attr[0].val.cooperative = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    attr[na].id = cudaLaunchAttributeCooperative;
+    attr[na].val.cooperative = 1;
+    ++na;
+    if (ctas == 2) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = 2;
+      attr[na].val.clusterDim.y = 1;
+      attr[na].val.clusterDim.z = 1;
+      ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    B200W_CUDA(cudaLaunchKernelEx(&cfg, tom_i8_kernel, tmap, prm));
+    cfg.numAttrs = na;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tmap, prm);
+    if (le != cudaSuccess) {
+      return fail(B200W_E_CUDA, "tom_i8: launch failed (%s), grid %d x %d threads, %d-CTA groups, %zu B smem",
+                  cudaGetErrorString(le), grid, kI8Threads, ctas, smem);
+    }
   }
   B200W_LAUNCHED();
   if (timed) {
