@@ -111,6 +111,15 @@ int b200w_network(const double* X, int64_t m, int64_t n, int net_type, double po
 int b200w_intramodular(const double* A, int64_t n, const int32_t* labels, int nmod,
                        const uint8_t* small, double* k_total, double* k_within, int device);
 
+/* Page-locked host buffers from a recycling pool, for the n x n results: a result written into
+ * such a buffer leaves the GPU by DMA at PCIe speed and, handed back as the input of the next call
+ * (adjacency -> TOMsimilarity), returns the same way.  Caller buffers that are NOT page-locked are
+ * accepted everywhere (they are page-locked for the duration of the call, or staged).
+ * b200w_host_free returns the buffer to the pool; b200w_host_trim releases the cached ones. */
+void* b200w_host_alloc(int64_t bytes);
+void b200w_host_free(void* p);
+void b200w_host_trim(void);
+
 /* ---------------------------------------------------------------- device entry points */
 
 /* bytes of scratch the dev_* calls need are allocated stream-ordered internally. */

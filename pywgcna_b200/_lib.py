@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -46,6 +47,9 @@ SIGNATURES = {
     "b200w_tom": (_int, [_dp, _i64, _int, _int, _int, _int, _i64, _i64, _dp, _int, _dp, _int]),
     "b200w_network": (_int, [_dp, _i64, _i64, _int, _dbl, _int, _int, _int, _int, _dp, _dp, _int]),
     "b200w_intramodular": (_int, [_dp, _i64, _dp, _int, _dp, _dp, _dp, _int]),
+    "b200w_host_alloc": (C.c_void_p, [_i64]),
+    "b200w_host_free": (None, [C.c_void_p]),
+    "b200w_host_trim": (None, []),
     "b200w_padded_k": (_i64, [_i64]),
     "b200w_dev_standardize": (_int, [_dp, _i64, _i64, _dp, _dp, _int, _dp]),
     "b200w_dev_sweep": (_int, [_dp, _dp, _i64, _i64, _dp, _int, _int, _i64, _i64, _dp, _int, _dp]),
@@ -100,6 +104,23 @@ def as_f64_matrix(x) -> np.ndarray:
     if a.ndim != 2:
         raise ValueError("expected a 2-D matrix")
     return a
+
+
+def result_empty(shape, dtype=np.float64) -> np.ndarray:
+    """Uninitialised C-contiguous array for a (large) result.  Arrays of 32 MB and more live in a
+    page-locked buffer of the library's recycling pool (DMA instead of staged copies, no first-touch
+    page faults); the buffer goes back to the pool when the last view of the array dies."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    if nbytes < (32 << 20) or os.environ.get("B200WGCNA_NO_PINNED_POOL"):
+        return np.empty(shape, dtype=dtype)
+    lib = load()
+    ptr = lib.b200w_host_alloc(nbytes)
+    if not ptr:
+        return np.empty(shape, dtype=dtype)
+    buf = (C.c_byte * nbytes).from_address(ptr)
+    weakref.finalize(buf, lib.b200w_host_free, ptr)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
 
 def device_count() -> int:

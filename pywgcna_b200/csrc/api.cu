@@ -2,8 +2,12 @@
 // These are what pywgcna_b200/wgcna.py binds behind WGCNA.pickSoftThreshold / adjacency /
 // TOMsimilarity: H2D of the caller's float64 buffers, the dev_* kernels, D2H of the result.
 #include <stdarg.h>
+#include <string.h>
+#include <sys/mman.h>
 
+#include <map>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -75,9 +79,107 @@ struct Stream {
   }
 };
 
+// ---- host memory -------------------------------------------------------------------------
+// (1) HostPin: page-locks a caller's (pageable) buffer for the duration of one call, so that the n x n
+//     transfers run as DMA at PCIe speed (measured on the B200 box: 3.2 GB pageable H2D 280 ms, fresh
+//     np.empty D2H 790 ms; cudaHostRegister 63 ms + 58 ms DMA + 47 ms unregister).
+// (2) a pool of page-locked buffers for the n x n RESULTS (b200w_host_alloc / b200w_host_free): first-touch
+//     page faults of a fresh 3.2 GB numpy array cost ~0.5 s and cudaHostAlloc 1.75 s, a recycled pinned
+//     buffer costs nothing and is written by DMA at 52 GB/s.
+struct HostPin {
+  void* p = nullptr;
+  void pin(const void* ptr, size_t bytes) {
+    if (!ptr || bytes < ((size_t)32 << 20)) return;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) == cudaSuccess && at.type != cudaMemoryTypeUnregistered) return;
+    cudaGetLastError();
+    if (cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterDefault) == cudaSuccess)
+      p = const_cast<void*>(ptr);
+    else
+      cudaGetLastError();  // fall back to a staged copy
+  }
+  ~HostPin() {
+    if (p) cudaHostUnregister(p);
+  }
+};
+
+struct HostPool {
+  std::mutex mu;
+  std::map<void*, size_t> live;                 // handed out: ptr -> bytes
+  std::map<void*, bool> registered;             // ptr -> page-locked?
+  std::vector<std::pair<size_t, void*>> free_;  // cached
+  size_t cached = 0;
+  size_t cap() {
+    const char* e = getenv("B200WGCNA_PINNED_POOL_MB");
+    return e ? (size_t)atoll(e) << 20 : (size_t)96 << 30;
+  }
+  void* alloc(size_t bytes) {
+    const size_t sz = (size_t)round_up((int64_t)(bytes ? bytes : 1), (int64_t)2 << 20);
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      for (size_t i = 0; i < free_.size(); ++i)
+        if (free_[i].first == sz) {
+          void* p = free_[i].second;
+          free_.erase(free_.begin() + i);
+          cached -= sz;
+          live[p] = sz;
+          return p;
+        }
+    }
+    void* p = mmap(nullptr, sz, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p == MAP_FAILED) return nullptr;
+    madvise(p, sz, MADV_HUGEPAGE);
+    // first touch in parallel (page faults are the cost, not the stores)
+    const unsigned nt = sz >= ((size_t)256 << 20) ? 8u : 1u;
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t)
+      th.emplace_back([=] {
+        char* b = (char*)p + sz / nt * t;
+        char* e = (t + 1 == nt) ? (char*)p + sz : b + sz / nt;
+        for (char* q = b; q < e; q += 4096) *q = 0;
+      });
+    for (auto& t : th) t.join();
+    bool reg = cudaHostRegister(p, sz, cudaHostRegisterPortable) == cudaSuccess;
+    if (!reg) cudaGetLastError();
+    std::lock_guard<std::mutex> lk(mu);
+    live[p] = sz;
+    registered[p] = reg;
+    return p;
+  }
+  void release(void* p, size_t sz) {
+    if (registered[p]) cudaHostUnregister(p);
+    registered.erase(p);
+    munmap(p, sz);
+  }
+  void free(void* p) {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = live.find(p);
+    if (it == live.end()) return;
+    const size_t sz = it->second;
+    live.erase(it);
+    if (cached + sz > cap()) {
+      release(p, sz);
+    } else {
+      free_.push_back({sz, p});
+      cached += sz;
+    }
+  }
+  void trim() {
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& f : free_) release(f.second, f.first);
+    free_.clear();
+    cached = 0;
+  }
+};
+static HostPool g_pool;
+
 }  // namespace b200w
 
 using namespace b200w;
+
+extern "C" void* b200w_host_alloc(int64_t bytes) { return bytes < 0 ? nullptr : g_pool.alloc((size_t)bytes); }
+extern "C" void b200w_host_free(void* p) { g_pool.free(p); }
+extern "C" void b200w_host_trim(void) { g_pool.trim(); }
 
 int b200w_dev_intramodular(const double* dA, int64_t n, const int32_t* d_labels,
                            const uint8_t* d_small, double* d_total, double* d_within,
@@ -138,6 +240,8 @@ extern "C" int b200w_adjacency(const double* X, int64_t m, int64_t n, int net_ty
   Stream st;
   B200W_CUDA(st.create());
   DevBuf dX, dZ, dBad, dA;
+  HostPin pin_out;
+  pin_out.pin(A_out, (size_t)nrows * n * 8);
   const int64_t ldk = b200w_padded_k(m);
   B200W_CUDA(dX.alloc((size_t)m * n * 8));
   B200W_CUDA(dZ.alloc((size_t)n * ldk * 8));
@@ -204,6 +308,9 @@ extern "C" int b200w_tom(const double* A, int64_t n, int tom_type, int tom_denom
   Stream st;
   B200W_CUDA(st.create());
   DevBuf dA;
+  HostPin pin_in, pin_out;
+  pin_in.pin(A, (size_t)n * n * 8);
+  pin_out.pin(out, (size_t)nrows * n * 8);
   B200W_CUDA(dA.alloc((size_t)n * n * 8));
   B200W_CUDA(cudaMemcpyAsync(dA.p, A, (size_t)n * n * 8, cudaMemcpyHostToDevice, st.s));
   if (check) {
@@ -232,6 +339,9 @@ extern "C" int b200w_network(const double* X, int64_t m, int64_t n, int net_type
   Stream st;
   B200W_CUDA(st.create());
   DevBuf dX, dZ, dBad, dA;
+  HostPin pin_a, pin_t;
+  pin_a.pin(A_out, (size_t)n * n * 8);
+  pin_t.pin(tom_out, (size_t)n * n * 8);
   const int64_t ldk = b200w_padded_k(m);
   B200W_CUDA(dX.alloc((size_t)m * n * 8));
   B200W_CUDA(dZ.alloc((size_t)n * ldk * 8));

@@ -24,6 +24,7 @@
 //            scratch (coalesced: lanes = rows), last pass applies (L + a) / (min(k_i,k_j) + 1 - a)
 #include <cuda.h>
 
+#include <map>
 #include <vector>
 
 #include "tom_common.cuh"
@@ -51,6 +52,9 @@ struct I8Params {
   double* scratch;       // gridDim.x * 128 * 256
   int64_t n, row0, nrows;
   int32_t tiles_m, tiles_n;
+  const int2* tile_list;  // (tm, tn) per tile, in an order that keeps co-resident tiles on shared panels
+  int32_t n_tiles;
+  int32_t symmetric;      // only tiles tn >= tm are listed; off-diagonal tiles are also stored mirrored
   int32_t nseg, npass;
   int32_t tom_type, tom_denom, out_mode, group;
   int32_t sync_mode;       // 0 none, 1 grid barrier of the producers per tile, 2 per segment
@@ -286,7 +290,7 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
   const bool leader = rank == 0;
   const int64_t unit = blockIdx.x / kCtas;           // CTA (pair) index
   const int64_t n_units = gridDim.x / kCtas;
-  const int64_t n_tiles = (int64_t)p.tiles_m * p.tiles_n;
+  const int64_t n_tiles = p.n_tiles;
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -331,7 +335,11 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
         const int64_t tile = unit + it * n_units;
         const bool active = tile < n_tiles;
         int64_t tm = 0, tn = 0;
-        if (active) grouped_tile(tile, p.tiles_m, p.tiles_n, p.group, tm, tn);
+        if (active) {
+          const int2 t2 = p.tile_list[tile];
+          tm = t2.x;
+          tn = t2.y;
+        }
         const int i0 = (int)(p.row0 + tm * Cfg::kTileRows + rank * kTM), j0 = (int)(tn * kTN);
         for (int sg = 0; sg < p.nseg; ++sg) {
           const Seg sgm = p.seg[sg];
@@ -427,9 +435,12 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
     for (int64_t it = 0; it < iters; ++it) {
       const int64_t tile = unit + it * n_units;
       if (tile >= n_tiles) break;
-      int64_t tm, tn;
-      grouped_tile(tile, p.tiles_m, p.tiles_n, p.group, tm, tn);
+      const int2 t2 = p.tile_list[tile];
+      const int64_t tm = t2.x, tn = t2.y;
       const int64_t gi = p.row0 + tm * Cfg::kTileRows + rank * kTM + row, j0 = tn * kTN;
+      // symmetric schedule: TOM_ji = TOM_ij, stored from the same registers; for a fixed column the 32
+      // lanes of a warp hold 32 consecutive rows, so the mirrored store is one coalesced 256-byte line
+      const bool mirror = p.symmetric && (tm * Cfg::kTileRows != tn * kTN);
       const bool row_ok = gi < p.row0 + p.nrows;
       const double ki = row_ok ? p.k[gi] : 0.0;
       const double si = row_ok ? p.scale[gi] * p.final_scale : 0.0;
@@ -461,7 +472,9 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
               if (row_ok && gj < p.n) {
                 const double L = v * (si * p.scale[gj]);
                 const double a = tom_clean(arow[gj], gi, gj);
-                orow[gj] = tom_value(L, a, ki, p.k[gj], gi == gj, p.tom_type, p.tom_denom, p.out_mode);
+                const double t = tom_value(L, a, ki, p.k[gj], gi == gj, p.tom_type, p.tom_denom, p.out_mode);
+                orow[gj] = t;
+                if (mirror) p.out[gj * p.n + gi] = t;
               }
             }
           }
@@ -589,8 +602,8 @@ int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t o
   prm.tom_type = tom_type;
   prm.tom_denom = tom_denom;
   prm.out_mode = out_mode;
-  prm.group = 16;
-  if (const char* e = getenv("B200W_I8_GROUP")) prm.group = atoi(e) > 0 ? atoi(e) : 16;
+  prm.group = 8;
+  if (const char* e = getenv("B200W_I8_GROUP")) prm.group = atoi(e) > 0 ? atoi(e) : 8;
   int w_min = kS - 1;
   if (const char* e = getenv("B200W_I8_WMIN")) w_min = atoi(e);
   if (w_min < 0 || w_min > 2 * (kS - 1)) return fail(B200W_E_INVALID, "tom_i8: bad B200W_I8_WMIN");
@@ -603,7 +616,40 @@ int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t o
   int dev = 0, sms = 0;
   B200W_CUDA(cudaGetDevice(&dev));
   B200W_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int64_t n_tiles = (int64_t)prm.tiles_m * prm.tiles_n;
+  // Tile schedule.  Whole matrix on one GPU with square 256 x 256 tiles: TOM is symmetric (A is, to
+  // 1e-12), so only the tiles on and above the diagonal are computed and mirrored -- half the MMAs.
+  // The list is ordered in square super-blocks of G x G tiles so that the ~74 co-resident tiles touch
+  // ~2G distinct operand panels.
+  bool symmetric = (ctas == 2) && row0 == 0 && nrows == n;
+  if (const char* e = getenv("B200W_I8_SYMMETRIC")) symmetric = symmetric && atoi(e) != 0;
+  // the list depends only on (device, TM, TN, G, symmetric): built and uploaded once, then cached
+  static std::map<std::vector<int>, std::pair<int2*, int>> tile_cache;
+  const std::vector<int> key = {dev, prm.tiles_m, prm.tiles_n, prm.group, symmetric ? 1 : 0};
+  auto hit = tile_cache.find(key);
+  if (hit == tile_cache.end()) {
+    std::vector<int2> tiles;
+    const int TM = prm.tiles_m, TN = prm.tiles_n;
+    int G = prm.group > 0 ? prm.group : 8;
+    if (symmetric) {
+      for (int bn = 0; bn * G < TN; ++bn)
+        for (int bm = 0; bm <= bn; ++bm)
+          for (int tn = bn * G; tn < TN && tn < (bn + 1) * G; ++tn)
+            for (int tm = bm * G; tm < TM && tm < (bm + 1) * G; ++tm)
+              if (tm <= tn) tiles.push_back(make_int2(tm, tn));
+    } else {
+      for (int bm = 0; bm * G < TM; ++bm)
+        for (int tn = 0; tn < TN; ++tn)
+          for (int tm = bm * G; tm < TM && tm < (bm + 1) * G; ++tm) tiles.push_back(make_int2(tm, tn));
+    }
+    int2* d_tiles = nullptr;
+    B200W_CUDA(cudaMalloc(&d_tiles, tiles.size() * sizeof(int2)));
+    B200W_CUDA(cudaMemcpy(d_tiles, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    hit = tile_cache.emplace(key, std::make_pair(d_tiles, (int)tiles.size())).first;
+  }
+  prm.symmetric = symmetric ? 1 : 0;
+  prm.n_tiles = hit->second.second;
+  prm.tile_list = hit->second.first;
+  const int64_t n_tiles = prm.n_tiles;
   const int64_t units = n_tiles < sms / ctas ? n_tiles : sms / ctas;
   const int grid = (int)(units * ctas);
   Scratch scratch;

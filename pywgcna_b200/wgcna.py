@@ -250,7 +250,7 @@ def adjacency(datExpr, selectCols=None, adjacencyType="unsigned", power=6, corOp
     X = L.as_f64_matrix(datExpr)
     m, n = X.shape
     row0, nrows = (0, n) if rows is None else (int(rows[0]), int(rows[1]))
-    out = np.empty((nrows, n), dtype=np.float64)
+    out = L.result_empty((nrows, n))
     L.check(L.load().b200w_adjacency(L.hptr(X), m, n, intType, float(power), row0, nrows, L.hptr(out),
                                      _device(device)))
     _say("\tDone..\n")
@@ -301,7 +301,7 @@ def _tom(adjMat, TOMTypeC, TOMDenomC, check, out_mode=L.OUT_TOM, device=None, ro
     A = np.ascontiguousarray(adjMat, dtype=np.float64)
     n = A.shape[0]
     row0, nrows = (0, n) if rows is None else (int(rows[0]), int(rows[1]))
-    out = np.empty((nrows, n), dtype=np.float64)
+    out = L.result_empty((nrows, n))
     stats = np.full(4, np.nan)
     prec = _PREC[(precision or PRECISION).lower()]
     rc = L.load().b200w_tom(L.hptr(A), n, TOMTypeC, TOMDenomC, out_mode, prec, row0, nrows, L.hptr(out),
@@ -335,7 +335,8 @@ def TOMsimilarity(adjMat, TOMType="signed", TOMDenom="min", device=None, precisi
     _say(f"{OKCYAN}calculating TOM similarity matrix ...{ENDC}")
     tom = _tom(adjMat, TOMTypeC, TOMDenomC, check=True, device=device, precision=precision)
     _say("\tDone..\n")
-    return pd.DataFrame(tom)
+    # copy=False: the reference's pandas (2.2) wraps the array; pandas >= 3 would copy n^2 doubles
+    return pd.DataFrame(tom, copy=False)
 
 
 def dissTOM(adjMat, TOMType="signed", TOMDenom="min", decimals=8, device=None, precision=None):
@@ -358,12 +359,12 @@ def network(datExpr, power=6, networkType="unsigned", TOMType="signed", TOMDenom
     TOMDenomC = TOMDenoms.index(TOMDenom)
     X = L.as_f64_matrix(datExpr)
     m, n = X.shape
-    A = np.empty((n, n), dtype=np.float64) if return_adjacency else None
-    T = np.empty((n, n), dtype=np.float64)
+    A = L.result_empty((n, n)) if return_adjacency else None
+    T = L.result_empty((n, n))
     prec = _PREC[(precision or PRECISION).lower()]
     L.check(L.load().b200w_network(L.hptr(X), m, n, intType, float(power), TOMTypeC, TOMDenomC, L.OUT_TOM, prec,
                                    L.hptr(A) if A is not None else None, L.hptr(T), _device(device)))
-    return A, pd.DataFrame(T)
+    return A, pd.DataFrame(T, copy=False)
 
 
 # ----------------------------------------------------------------------------------------------
