@@ -153,10 +153,16 @@ def test_oracle_tom(gpu, prec, n):
             T = bw.TOMsimilarity(A.copy(), TOMType=tt, TOMDenom=td, precision=prec).to_numpy()
             assert maxabs(T, T_ref) < TOL_TOM[prec], (net, tt, td)
             assert np.all(np.diag(T) == 1.0)
-    # row block == slice of the full result; fused dissTOM == (1 - TOM).round(8)
-    T = bw.TOMsimilarity(A.copy(), precision=prec).to_numpy()
-    blk = bw.wgcna._tom(A.copy(), 1, 0, check=False, rows=(n // 4, n // 2), precision=prec)
+    # row block == slice of the full result; fused dissTOM == (1 - TOM).round(8).
+    # np.corrcoef's output is asymmetric in the last bit; the whole-matrix int8 schedule computes the
+    # upper triangle and mirrors it (TOM_ji := TOM_ij), a row block computes every entry from its own
+    # a_ij -- so the two agree exactly only for an exactly symmetric input.
+    As = np.maximum(A, A.T)
+    T = bw.TOMsimilarity(As.copy(), precision=prec).to_numpy()
+    blk = bw.wgcna._tom(As.copy(), 1, 0, check=False, rows=(n // 4, n // 2), precision=prec)
     assert np.array_equal(blk, T[n // 4:n // 4 + n // 2])
+    assert np.array_equal(T, T.T)
+    A = As
     D = bw.dissTOM(A.copy(), precision=prec)
     assert np.array_equal(D, (1 - T).round(decimals=8))
 
