@@ -58,15 +58,21 @@ standardize_kernel(const double* __restrict__ X, int64_t m, int64_t n, int64_t l
     __syncwarp();
   }
 }
-
 // -------------------------------------------------------------------------------------------
-// K2  fused soft-threshold sweep.  CTA (jt, rc) owns the 128 genes of column tile jt and the row
-// tiles it = rc, rc + R, ... ; for each it computes the 128 x 128 correlation tile on the DMMA
-// pipe and, while it is still in registers, evaluates the similarity transform and the running
+// K2  fused soft-threshold sweep.  The work is the CT x RT grid of 128 x 128 correlation tiles
+// (CT column tiles of the genes whose connectivity is wanted, RT row tiles of all genes), taken
+// column-major and cut into one contiguous, equally long range per CTA (persistent, one CTA per SM:
+// no tail wave).  For each tile the CTA computes Z_i Z_j^T on the DMMA pipe and, while the tile is
+// still in registers, evaluates clip -> similarity transform -> diag <- 1 -> NaN skip -> the running
 // product chain for all P powers, reducing over rows.  The n x n matrix is never written.
-// Column sums accumulate in shared memory with exactly one owner lane per (warp row, power, column),
-// and the R partial results are summed in fixed order by sweep_reduce_kernel: the result is
-// deterministic and independent of the launch geometry of other CTAs.
+// Column sums accumulate in shared memory with exactly one owner lane per (warp row, power, column);
+// whenever the range crosses into the next column tile the sums are flushed to a partial slot, and
+// sweep_reduce_kernel adds the slots of a column tile in CTA order: deterministic, no atomics.
+//
+// Epilogue shape: a quarter of the warp's 64 x 32 sub-tile (8 columns = 2 per thread, 8 rows each) is
+// processed at a time; the transformed similarities overwrite the accumulator registers, the 16
+// running products live in registers, and per power the 2 column sums go through tree adds and
+// three shuffle rounds together, so their latencies overlap.
 // -------------------------------------------------------------------------------------------
 constexpr int kSweepStages = 3;
 constexpr int kSweepMaxP = 32;
@@ -76,14 +82,19 @@ struct SweepParams {
   const uint8_t* bad;
   int64_t n, ldk;
   int64_t col0, ncols;  // genes whose connectivity this launch produces
+  int64_t RT, T;        // row tiles, total tiles (CT * RT)
   int P;
   int net_type;
-  int R;             // row chunks
-  double* partial;   // [R][P][ncols_pad]
-  int64_t ncols_pad;
+  int max_seg;          // partial slots per CTA
+  double* partial;      // [gridDim.x][max_seg][P][128]
   double step[kSweepMaxP];
   int istep[kSweepMaxP];
 };
+
+__device__ __forceinline__ void sweep_range(int64_t T, int64_t G, int64_t b, int64_t& t0, int64_t& t1) {
+  t0 = T * b / G;
+  t1 = T * (b + 1) / G;
+}
 
 __global__ void __launch_bounds__(kGemmThreads, 1) sweep_kernel(const SweepParams prm) {
   extern __shared__ __align__(16) double smem[];
@@ -94,19 +105,30 @@ __global__ void __launch_bounds__(kGemmThreads, 1) sweep_kernel(const SweepParam
   const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, tig = lane & 3;
   const int P = prm.P;
   const int64_t n = prm.n;
-  const int64_t j0 = prm.col0 + (int64_t)blockIdx.x * kBN;  // first gene of the column tile
   const int64_t jend = prm.col0 + prm.ncols;
+  int64_t t0, t1;
+  sweep_range(prm.T, gridDim.x, blockIdx.x, t0, t1);
+  if (t0 >= t1) return;
+  const int64_t jt_first = t0 / prm.RT;
+  int64_t cur_jt = -1;
 
-  for (int i = threadIdx.x; i < 2 * P * kBN; i += kGemmThreads) colacc[i] = 0.0;
-  if (threadIdx.x < kBN) {
-    int64_t j = j0 + threadIdx.x;
-    bad_col[threadIdx.x] = (j < jend) ? prm.bad[j] : 1;
-  }
-  __syncthreads();
-
-  const int64_t n_row_tiles = (n + kBM - 1) / kBM;
-  for (int64_t it = blockIdx.y; it < n_row_tiles; it += prm.R) {
-    const int64_t i0 = it * kBM;
+  for (int64_t t = t0; t < t1; ++t) {
+    const int64_t jt = t / prm.RT, it = t - jt * prm.RT;
+    const int64_t j0 = prm.col0 + jt * kBN, i0 = it * kBM;
+    if (jt != cur_jt) {  // entering a new column tile: flush the previous one, reset the sums
+      __syncthreads();
+      if (cur_jt >= 0) {
+        double* dst = prm.partial + ((int64_t)blockIdx.x * prm.max_seg + (cur_jt - jt_first)) * P * kBN;
+        for (int i = threadIdx.x; i < P * kBN; i += kGemmThreads) dst[i] = colacc[i] + colacc[P * kBN + i];
+        __syncthreads();
+      }
+      for (int i = threadIdx.x; i < 2 * P * kBN; i += kGemmThreads) colacc[i] = 0.0;
+      if (threadIdx.x < kBN) {
+        int64_t j = j0 + threadIdx.x;
+        bad_col[threadIdx.x] = (j < jend) ? prm.bad[j] : 1;
+      }
+      cur_jt = jt;
+    }
     if (threadIdx.x < kBM) {
       int64_t i = i0 + threadIdx.x;
       bad_row[threadIdx.x] = (i < n) ? prm.bad[i] : 1;
@@ -115,88 +137,144 @@ __global__ void __launch_bounds__(kGemmThreads, 1) sweep_kernel(const SweepParam
     acc.clear();
     // rows of the tile = genes i (summed over), columns = genes j (kept)
     gemm_f64_tile<kSweepStages>(acc, smem, prm.Z, prm.Z, prm.ldk, prm.ldk, i0, n, j0, n);
-    // (gemm_f64_tile ends with a __syncthreads, so bad_row is visible)
+    // (gemm_f64_tile ends with a __syncthreads, so bad_row / bad_col / the zeroed sums are visible)
 
 #pragma unroll
     for (int ni = 0; ni < 4; ++ni) {
+      double cur[16];
+      // element e = (cb * 4 + mi) * 2 + ch  ->  acc.v[mi][ni][ch * 2 + cb]
 #pragma unroll
       for (int cb = 0; cb < 2; ++cb) {
         const int col = wn * 32 + ni * 8 + 2 * tig + cb;
         const int64_t gj = j0 + col;
         const bool cbad = bad_col[col];
-        double s[8], cur[8];
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi) {
+        for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
           for (int ch = 0; ch < 2; ++ch) {
             const int row = wm * 64 + mi * 16 + g + ch * 8;
             const int64_t gi = i0 + row;
             double c = acc.v[mi][ni][ch * 2 + cb];
-            c = fmin(1.0, fmax(-1.0, c));                  // np.corrcoef clips to [-1, 1]
-            double sv = net_transform(c, prm.net_type);    // wgcna.py:884-889
+            c = fmin(1.0, fmax(-1.0, c));                // np.corrcoef clips to [-1, 1]
+            double sv = net_transform(c, prm.net_type);  // wgcna.py:884-889
             double c0 = 1.0;
-            if (gi == gj) sv = 1.0;                        // wgcna.py:897 (even for a NaN gene)
+            if (gi == gj) sv = 1.0;                      // wgcna.py:897 (even for a NaN gene)
             else if (cbad || bad_row[row]) { sv = 0.0; c0 = 0.0; }  // NaN: skipped by nansum :915
             if (gi >= n) { sv = 0.0; c0 = 0.0; }
-            s[mi * 2 + ch] = sv;
-            cur[mi * 2 + ch] = c0;
+            acc.v[mi][ni][ch * 2 + cb] = sv;
+            cur[(cb * 4 + mi) * 2 + ch] = c0;
           }
-        }
-        for (int p = 0; p < P; ++p) {
-          const double st = prm.step[p];
-          const int ist = prm.istep[p];
-          double v = 0.0;
+      }
+#pragma unroll 1
+      for (int p = 0; p < P; ++p) {
+        const int ist = prm.istep[p];
+        // wgcna.py:914  corxCur = corxPrev * corx ** step
+        if (ist == 1) {
 #pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            cur[r] *= step_pow(s[r], st, ist);  // wgcna.py:914  corxCur = corxPrev * corx**step
-            v += cur[r];
-          }
-          v += __shfl_xor_sync(0xffffffffu, v, 4);
-          v += __shfl_xor_sync(0xffffffffu, v, 8);
-          v += __shfl_xor_sync(0xffffffffu, v, 16);
-          if (g == 0) colacc[(wm * P + p) * kBN + col] += v;
+          for (int cb = 0; cb < 2; ++cb)
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+              for (int ch = 0; ch < 2; ++ch) cur[(cb * 4 + mi) * 2 + ch] *= acc.v[mi][ni][ch * 2 + cb];
+        } else {
+          const double st = prm.step[p];
+#pragma unroll
+          for (int cb = 0; cb < 2; ++cb)
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+              for (int ch = 0; ch < 2; ++ch)
+                cur[(cb * 4 + mi) * 2 + ch] *= step_pow(acc.v[mi][ni][ch * 2 + cb], st, ist);
+        }
+        double v[2];
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb) {
+          const double* q = cur + cb * 8;
+          v[cb] = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
+        }
+#pragma unroll
+        for (int o = 4; o <= 16; o <<= 1)
+#pragma unroll
+          for (int cb = 0; cb < 2; ++cb) v[cb] += __shfl_xor_sync(0xffffffffu, v[cb], o);
+        if (g == 0) {
+#pragma unroll
+          for (int cb = 0; cb < 2; ++cb)
+            colacc[(wm * P + p) * kBN + wn * 32 + ni * 8 + 2 * tig + cb] += v[cb];
         }
       }
     }
-    __syncthreads();  // bad_row is rewritten by the next iteration
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < P * kBN; i += kGemmThreads) {
-    int p = i / kBN, col = i % kBN;
-    int64_t jj = (int64_t)blockIdx.x * kBN + col;
-    if (jj < prm.ncols)
-      prm.partial[((int64_t)blockIdx.y * P + p) * prm.ncols_pad + jj] =
-          colacc[p * kBN + col] + colacc[(P + p) * kBN + col];
+  {
+    double* dst = prm.partial + ((int64_t)blockIdx.x * prm.max_seg + (cur_jt - jt_first)) * P * kBN;
+    for (int i = threadIdx.x; i < P * kBN; i += kGemmThreads) dst[i] = colacc[i] + colacc[P * kBN + i];
   }
 }
 
-// k[p][j] = sum_r partial[r][p][j] - 1      (wgcna.py:915  nansum(...) - 1)
-__global__ void sweep_reduce_kernel(const double* __restrict__ partial, int R, int P,
-                                    int64_t ncols, int64_t ncols_pad, double* __restrict__ k) {
-  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int p = blockIdx.y;
+// k[p][j] = sum over the CTAs whose range covers column tile jt of their slot - 1   (wgcna.py:915)
+__global__ void sweep_reduce_kernel(const double* __restrict__ partial, int G, int max_seg, int P,
+                                    int64_t RT, int64_t T, int64_t ncols, double* __restrict__ k) {
+  const int64_t jt = blockIdx.x;
+  const int col = threadIdx.x;  // 128
+  const int p = blockIdx.y;
+  const int64_t j = jt * kBN + col;
   if (j >= ncols) return;
+  const int64_t lo = jt * RT, hi = lo + RT;  // tiles of this column tile
   double s = 0.0;
-  for (int r = 0; r < R; ++r) s += partial[((int64_t)r * P + p) * ncols_pad + j];
+  for (int64_t b = lo * G / T; b < G; ++b) {
+    int64_t t0, t1;
+    sweep_range(T, G, b, t0, t1);
+    if (t0 >= hi) break;
+    if (t1 <= lo || t0 >= t1) continue;
+    const int64_t seg = jt - t0 / RT;
+    s += partial[(((int64_t)b * max_seg + seg) * P + p) * kBN + col];
+  }
   k[(int64_t)p * ncols + j] = s - 1.0;
 }
 
 // -------------------------------------------------------------------------------------------
-// K1 + K3  adjacency: correlation tile on the DMMA pipe, epilogue clip -> transform -> pow(., power)
+// K1 + K3  adjacency: correlation tile on the DMMA pipe, epilogue clip -> transform -> s ** power
 // (wgcna.py:1097-1111).  Rows of a NaN gene are NaN, as np.corrcoef makes them; the diagonal is not
 // forced (the reference leaves it at corrcoef's value).  Output rows [row0, row0 + nrows).
+// Whole matrix (row0 = 0, nrows = n): only tiles on and above the diagonal are computed, every
+// off-diagonal tile is stored twice (cor is symmetric: the same dot product), which also makes the
+// result exactly symmetric -- checkAdjMat's 1e-12 test (wgcna.py:1135) passes with margin.
+// Small integer powers are evaluated by repeated squaring (<= 2 ulp from libm's pow).
 // -------------------------------------------------------------------------------------------
 constexpr int kAdjStages = 4;
+
+__device__ __forceinline__ double int_pow(double s, int e) {
+  double r = 1.0, b = s;
+#pragma unroll 1
+  while (e) {
+    if (e & 1) r *= b;
+    b *= b;
+    e >>= 1;
+  }
+  return r;
+}
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
 adjacency_kernel(const double* __restrict__ Z, const uint8_t* __restrict__ bad, int64_t n,
                  int64_t ldk, int net_type, double power, int ipower, int64_t row0, int64_t nrows,
-                 double* __restrict__ A) {
+                 int symmetric, int64_t tiles_n, double* __restrict__ A) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, tig = lane & 3;
-  const int64_t i0 = row0 + (int64_t)blockIdx.y * kBM, j0 = (int64_t)blockIdx.x * kBN;
+  int64_t ti, tj;
+  if (symmetric) {  // blockIdx.x enumerates the upper triangle row by row
+    int64_t t = blockIdx.x, T = tiles_n;
+    ti = (int64_t)floor((2.0 * T + 1.0 - sqrt((2.0 * T + 1.0) * (2.0 * T + 1.0) - 8.0 * (double)t)) / 2.0);
+    while (ti > 0 && ti * T - ti * (ti - 1) / 2 > t) --ti;
+    while ((ti + 1) * T - (ti + 1) * ti / 2 <= t) ++ti;
+    tj = ti + (t - (ti * T - ti * (ti - 1) / 2));
+  } else {
+    ti = blockIdx.x / tiles_n;
+    tj = blockIdx.x % tiles_n;
+  }
+  const int64_t i0 = row0 + ti * kBM, j0 = tj * kBN;
   const int64_t iend = row0 + nrows;
+  const bool mirror = symmetric && ti != tj;
 
   AccF64 acc;
   acc.clear();
@@ -221,11 +299,11 @@ adjacency_kernel(const double* __restrict__ Z, const uint8_t* __restrict__ bad, 
           c = fmin(1.0, fmax(-1.0, c));
           double s = net_transform(c, net_type);
           double a;
-          if (ipower == 1) a = s;
-          else if (ipower == 2) a = s * s;
+          if (ipower > 0) a = int_pow(s, ipower);
           else a = pow(s, power);
           if (rbad || bad[gj]) a = qnan;
           out[gj] = a;
+          if (mirror) A[gj * n + gi] = a;
         }
       }
     }
@@ -261,29 +339,23 @@ extern "C" int b200w_dev_sweep(const double* dZ, const uint8_t* d_bad, int64_t m
   if (int e = ensure_device(device)) return e;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t ldk = b200w_padded_k(m);
-  const int64_t col_tiles = (ncols + kBN - 1) / kBN, row_tiles = (n + kBM - 1) / kBM;
-  const int64_t ncols_pad = col_tiles * kBN;
-  // row chunks: enough CTAs for >= 2 waves of 148 SMs, never more than there are row tiles
-  int R = (int)((2 * 148 + col_tiles - 1) / col_tiles);
-  if (R > row_tiles) R = (int)row_tiles;
-  if (R < 1) R = 1;
-  if (R > 65535) R = 65535;
+  const int64_t CT = (ncols + kBN - 1) / kBN, RT = (n + kBM - 1) / kBM, T = CT * RT;
+  int sms = 0;
+  B200W_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const int G = (int)(T < sms ? T : sms);  // persistent: one CTA per SM, equal tile ranges
+  const int max_seg = (int)((T / G + 1 + RT - 1) / RT + 1);
 
-  static bool attr_set = false;
   const size_t smem_max = gemm_smem_bytes(kSweepStages) + (size_t)2 * kSweepMaxP * kBN * 8;
-  if (!attr_set) {
-    B200W_CUDA(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)smem_max));
-    attr_set = true;
-  }
+  B200W_CUDA(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem_max));
   for (int p0 = 0; p0 < P; p0 += kSweepMaxP) {
-    // the chain restarts from 1 for each chunk, so the first step of a later chunk is the whole
-    // power reached so far; that needs pow() with a large exponent, which is the same value the
-    // reference's chain approximates to ~1e-15.
+    // the chain restarts from 1 for each chunk of 32 powers, so the first step of a later chunk is
+    // the whole power reached so far (pow() with a large exponent: the value the reference's chain
+    // approximates to ~1e-15).
     const int Pc = (P - p0 < kSweepMaxP) ? P - p0 : kSweepMaxP;
     SweepParams prm;
     prm.Z = dZ; prm.bad = d_bad; prm.n = n; prm.ldk = ldk; prm.col0 = col0; prm.ncols = ncols;
-    prm.P = Pc; prm.net_type = net_type; prm.R = R; prm.ncols_pad = ncols_pad;
+    prm.RT = RT; prm.T = T; prm.P = Pc; prm.net_type = net_type; prm.max_seg = max_seg;
     double base = 0.0;
     for (int q = 0; q < p0; ++q) base += h_steps[q];
     for (int q = 0; q < Pc; ++q) {
@@ -292,14 +364,13 @@ extern "C" int b200w_dev_sweep(const double* dZ, const uint8_t* d_bad, int64_t m
       prm.istep[q] = (s == (double)(int)s && s >= 1.0 && s <= 4.0) ? (int)s : 0;
     }
     Scratch part;
-    B200W_CUDA(part.alloc((size_t)R * Pc * ncols_pad * sizeof(double), st));
+    B200W_CUDA(part.alloc((size_t)G * max_seg * Pc * kBN * sizeof(double), st));
     prm.partial = part.as<double>();
     const size_t smem = gemm_smem_bytes(kSweepStages) + (size_t)2 * Pc * kBN * 8;
-    dim3 grid((unsigned)col_tiles, (unsigned)R);
-    sweep_kernel<<<grid, kGemmThreads, smem, st>>>(prm);
+    sweep_kernel<<<G, kGemmThreads, smem, st>>>(prm);
     B200W_LAUNCHED();
-    dim3 rgrid((unsigned)((ncols + 255) / 256), (unsigned)Pc);
-    sweep_reduce_kernel<<<rgrid, 256, 0, st>>>(prm.partial, R, Pc, ncols, ncols_pad,
+    dim3 rgrid((unsigned)CT, (unsigned)Pc);
+    sweep_reduce_kernel<<<rgrid, kBN, 0, st>>>(prm.partial, G, max_seg, Pc, RT, T, ncols,
                                                d_k + (int64_t)p0 * ncols);
     B200W_LAUNCHED();
   }
@@ -314,19 +385,17 @@ extern "C" int b200w_dev_adjacency(const double* dZ, const uint8_t* d_bad, int64
   if (net_type < 0 || net_type > 2) return fail(B200W_E_INVALID, "adjacency: bad network type");
   if (int e = ensure_device(device)) return e;
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_set = false;
   const size_t smem = gemm_smem_bytes(kAdjStages);
-  if (!attr_set) {
-    B200W_CUDA(cudaFuncSetAttribute(adjacency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)smem));
-    attr_set = true;
-  }
-  int ipower = (power == 1.0) ? 1 : (power == 2.0) ? 2 : 0;
-  int64_t row_tiles = (nrows + kBM - 1) / kBM, col_tiles = (n + kBN - 1) / kBN;
-  if (row_tiles > 65535) return fail(B200W_E_UNSUPPORTED, "adjacency: too many row tiles");
-  dim3 grid((unsigned)col_tiles, (unsigned)row_tiles);
-  adjacency_kernel<<<grid, kGemmThreads, smem, st>>>(dZ, d_bad, n, b200w_padded_k(m), net_type,
-                                                     power, ipower, row0, nrows, dA);
+  B200W_CUDA(cudaFuncSetAttribute(adjacency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+  int ipower = (power == (double)(int)power && power >= 1.0 && power <= 64.0) ? (int)power : 0;
+  const int64_t row_tiles = (nrows + kBM - 1) / kBM, col_tiles = (n + kBN - 1) / kBN;
+  const int symmetric = (row0 == 0 && nrows == n) ? 1 : 0;
+  const int64_t blocks = symmetric ? col_tiles * (col_tiles + 1) / 2 : row_tiles * col_tiles;
+  if (blocks > 2147483647LL) return fail(B200W_E_UNSUPPORTED, "adjacency: too many tiles");
+  adjacency_kernel<<<(unsigned)blocks, kGemmThreads, smem, st>>>(dZ, d_bad, n, b200w_padded_k(m),
+                                                                  net_type, power, ipower, row0, nrows,
+                                                                  symmetric, col_tiles, dA);
   B200W_LAUNCHED();
   return 0;
 }
