@@ -224,11 +224,7 @@ def run_ours(args):
         k = net_dev.sweep(powers)  # [P, n] on device
         k_host = k.cpu().numpy()  # D2H of the connectivities (P * n * 8 bytes)
         pv = np.sort(np.asarray(powers))
-        r2 = np.empty(P)
-        mk = np.empty(P)
-        for i in range(P):
-            r2[i] = W._scale_free_fit(k_host[i], 10)[0]
-            mk[i] = float(W._exact_mean(k_host[i]))
+        r2, _, _, mk, _, _ = W.fit_table(k_host, 10)  # the whole sft table of wgcna.py:924-932
         ind = (r2 > 0.9) & (mk <= 100)
         power = int(pv[ind].min()) if ind.any() else int(pv[np.argsort(r2)[-1]])
         net_dev.adjacency(power)

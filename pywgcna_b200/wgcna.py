@@ -137,6 +137,98 @@ def _exact_mean(k: np.ndarray) -> np.float64:
     return np.float64(float((Fraction(s) + Fraction(r)) / len(vals)))
 
 
+def _exact_mean_sorted(ks: np.ndarray) -> np.float64:
+    """Same value as ``_exact_mean`` (= ``statistics.mean``), vectorised: every double is
+    mantissa * 2^exponent with a 53-bit integer mantissa; mantissas are summed exactly per exponent
+    (split in 27-bit halves so float64 bincount sums stay below 2^53), the few per-exponent totals are
+    combined as Python integers and the exact rational sum / n is rounded once."""
+    n = ks.shape[0]
+    if n == 0 or not np.isfinite(ks[0]) or not np.isfinite(ks[-1]):
+        return _exact_mean(ks)
+    m, e = np.frexp(ks)
+    M = (m * 9007199254740992.0).astype(np.int64)  # m * 2^53, exact
+    nz = M != 0
+    if not nz.any():
+        return np.float64(0.0)
+    emin = int(e[nz].min())
+    sh = np.where(nz, e - emin, 0).astype(np.int64)
+    hi = M >> 27
+    lo = M - (hi << 27)
+    W = int(sh.max()) + 1
+    slo = np.bincount(sh, weights=lo.astype(np.float64), minlength=W)
+    shi = np.bincount(sh, weights=hi.astype(np.float64), minlength=W)
+    total = 0
+    for s in np.nonzero((slo != 0) | (shi != 0))[0].tolist():
+        total += ((int(shi[s]) << 27) + int(slo[s])) << s
+    ex = emin - 53
+    frac = Fraction(total * (1 << ex), n) if ex >= 0 else Fraction(total, n * (1 << -ex))
+    return np.float64(float(frac))
+
+
+def _ols_batch(y: np.ndarray, X: np.ndarray):
+    """``_ols`` for a stack of problems: y [B, N], X [B, N, q] -> params [B, q], R^2 [B], adj R^2 [B]
+    (pinv and rank from one batched SVD, like statsmodels' pinv solve + matrix_rank)."""
+    with np.errstate(all="ignore"):
+        pinv = np.linalg.pinv(X)
+        beta = np.einsum("bqn,bn->bq", pinv, y)
+        resid = y - np.einsum("bnq,bq->bn", X, beta)
+        ssr = np.einsum("bn,bn->b", resid, resid)
+        yc = y - y.mean(axis=1, keepdims=True)
+        tss = np.einsum("bn,bn->b", yc, yc)
+        rsq = 1.0 - ssr / tss
+        rank = np.linalg.matrix_rank(X)
+        nobs = y.shape[1]
+        rsq_adj = 1.0 - (nobs - 1) / (nobs - rank) * (1.0 - rsq)
+    return beta, rsq, rsq_adj
+
+
+def fit_table(K: np.ndarray, nBreaks: int = 10):
+    """All per-power statistics of wgcna.py:924-932 for k[P, n] at once: returns the arrays
+    (SFT.R.sq, slope, truncated R.sq, mean(k), median(k), max(k)).  Same arithmetic as
+    ``scaleFreeFitIndex`` / ``statistics.mean`` / ``statistics.median``; one sort per power serves the
+    median, the histogram (bin boundaries by binary search of the 11 edges in the sorted k) and the
+    exact mean, and the 2 x P least-squares problems are solved as two batched SVDs."""
+    K = np.asarray(K, dtype=np.float64)
+    P, n = K.shape
+    dk = np.empty((P, nBreaks))
+    p_dk = np.empty((P, nBreaks))
+    mean = np.empty(P)
+    med = np.empty(P)
+    mx = np.empty(P)
+    with np.errstate(all="ignore"):
+        for i in range(P):
+            ks = np.sort(K[i])
+            lo_, hi_ = float(ks[0]), float(ks[-1])
+            mx[i] = hi_
+            med[i] = ks[n // 2] if n % 2 else (ks[n // 2 - 1] + ks[n // 2]) / 2  # statistics.median
+            mean[i] = _exact_mean_sorted(ks)
+            edges = _cut_edges(lo_, hi_, nBreaks)
+            # bin b = (edges[b], edges[b+1]]  ->  boundaries = #elements <= edge
+            bnd = np.searchsorted(ks, edges, side="right")  # bnd[0] = 0 and bnd[-1] = n by construction
+            cnt = np.diff(bnd).astype(np.float64)
+            tot = np.zeros(nBreaks)
+            ne = np.nonzero(cnt > 0)[0]
+            # the non-empty bins tile the sorted array contiguously, so reduceat over their starts sums
+            # exactly the members of each bin
+            tot[ne] = np.add.reduceat(ks, bnd[ne])
+            d = tot / cnt  # NaN where a bin is empty (:1019)
+            mids = np.linspace(lo_, hi_, nBreaks + 1)  # (:1025)
+            mids = 0.5 * (mids[1:] + mids[:-1])  # (:1027)
+            empty = np.isnan(d)
+            d[empty] = mids[empty]  # (:1029-1030)
+            zero = d == 0
+            d[zero] = mids[zero]  # (:1031-1032)
+            dk[i] = d
+            p_dk[i] = cnt / n  # (:1022)
+        log_dk = np.log10(dk)  # (:1035)
+        log_p = np.log10(p_dk + 1e-09)  # (:1036)
+        trunc = np.power(10, log_dk)  # (:1037)
+        ones = np.ones_like(log_dk)
+        b1, r1, _ = _ols_batch(log_p, np.stack([ones, log_dk], axis=2))  # (:1039)
+        _, _, r2adj = _ols_batch(log_p, np.stack([ones, log_dk, trunc], axis=2))  # (:1040)
+    return r1, b1[:, 1], r2adj, mean, med, mx
+
+
 def calBlockSize(matrixSize, rectangularBlocks=True, maxMemoryAllocation=None, overheadFactor=3):
     """``WGCNA.calBlockSize`` (wgcna.py:988-1004).  Only reported for log parity: the CUDA sweep
     tiles the n x n problem on chip and needs no host block size."""
@@ -206,15 +298,10 @@ def pickSoftThreshold(data, dataIsExpr=True, weights=None, RsquaredCut=0.9, Mean
 
     datk = connectivity(data, powerVector, networkType, device=device)
 
-    for i in range(len(powerVector)):  # :924-932
-        khelp = np.ascontiguousarray(datk[:, i])
-        r1, slope, r2adj = _scale_free_fit(khelp, nBreaks)
-        datout.loc[i, "SFT.R.sq"] = r1
-        datout.loc[i, "slope"] = slope
-        datout.loc[i, "truncated R.sq"] = r2adj
-        datout.loc[i, "mean(k)"] = _exact_mean(khelp)
-        datout.loc[i, "median(k)"] = np.median(khelp)
-        datout.loc[i, "max(k)"] = khelp.max()
+    # :924-932, all powers at once (datk is the transpose view of the kernel's [P, n] output)
+    stats = fit_table(np.ascontiguousarray(datk.T), nBreaks)
+    for name, col in zip(colname1[1:], stats):
+        datout[name] = pd.Series(list(col), dtype=object)
     _say(datout)
 
     # :945-953 -- raw R^2, not the slope-signed one

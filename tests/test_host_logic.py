@@ -31,6 +31,21 @@ def test_exact_mean_equals_statistics_mean():
         assert float(W._exact_mean(k)) == float(statistics.mean(k))
 
 
+def test_fit_table_matches_scalar_path_and_statistics():
+    rng = np.random.default_rng(4)
+    K = rng.gamma(2.0, 30.0, size=(6, 3001))
+    K[1] *= 1e-9
+    K[2, :3] = 0.0
+    K[3] = np.concatenate([rng.uniform(0, 1, 2998), [50.0, 51.0, 100.0]])  # leaves bins empty
+    K[4] = 2.5  # min == max branch of pd.cut
+    K[5, 0] = -1e-17  # nansum(...) - 1 can come out a hair below zero
+    r2, slope, r2adj, mean, med, mx = W.fit_table(K)
+    for i in range(len(K)):
+        ref = W._scale_free_fit(K[i], 10)
+        np.testing.assert_allclose([r2[i], slope[i], r2adj[i]], ref, rtol=1e-9, atol=1e-12)
+        assert mean[i] == statistics.mean(K[i]) and med[i] == statistics.median(K[i]) and mx[i] == max(K[i])
+
+
 def test_cal_block_size():
     assert bw.calBlockSize(20000, True, 2 ** 30) == 2236
     assert bw.calBlockSize(23844, True, 2 ** 30) == 1876  # C1
