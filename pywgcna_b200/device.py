@@ -15,20 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
-
-
-def rows_per_rank(n: int, world: int, align: int = 128) -> int:
-    """Rows every rank owns (the last ranks may own fewer or none): ceil(n / world) rounded up to
-    the operand tile height, so every block starts on a tile boundary."""
-    per = -(-n // world)
-    return -(-per // align) * align
-
-
-def row_block(n: int, world: int, rank: int, align: int = 128):
-    per = rows_per_rank(n, world, align)
-    r0 = min(n, rank * per)
-    r1 = min(n, r0 + per)
-    return r0, r1 - r0
+from .shard import all_gather_rows, row_block, rows_per_rank
 
 
 class DeviceNetwork:
@@ -78,12 +65,7 @@ class DeviceNetwork:
 
     def _all_gather_rows(self, full: torch.Tensor):
         """In-place all-gather of the ``per``-row blocks of ``full`` ([op_rows, ...], contiguous)."""
-        if self.world == 1:
-            return
-        import torch.distributed as dist
-
-        mine = full[self.rank * self.per:(self.rank + 1) * self.per]
-        dist.all_gather_into_tensor(full, mine, group=self.group)
+        all_gather_rows(full, self.per, self.rank, self.world, self.group)
 
     # -- the three stages ------------------------------------------------------------------
     def sweep(self, powers) -> torch.Tensor:
