@@ -440,7 +440,8 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
       const int64_t gi = p.row0 + tm * Cfg::kTileRows + rank * kTM + row, j0 = tn * kTN;
       // symmetric schedule: TOM_ji = TOM_ij, stored from the same registers; for a fixed column the 32
       // lanes of a warp hold 32 consecutive rows, so the mirrored store is one coalesced 256-byte line
-      const bool mirror = p.symmetric && (tm * Cfg::kTileRows != tn * kTN);
+      // (in a diagonal tile only the entries on and above the diagonal are stored, with their mirror)
+      const bool mirror = p.symmetric != 0;
       const bool row_ok = gi < p.row0 + p.nrows;
       const double ki = row_ok ? p.k[gi] : 0.0;
       const double si = row_ok ? p.scale[gi] * p.final_scale : 0.0;
@@ -469,12 +470,12 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
               double v = (double)(int)r[col] * w;
               if (!first) v += sc[col * kTM];
               const int64_t gj = j0 + c * 32 + col;
-              if (row_ok && gj < p.n) {
+              if (row_ok && gj < p.n && !(mirror && gj < gi)) {
                 const double L = v * (si * p.scale[gj]);
                 const double a = tom_clean(arow[gj], gi, gj);
                 const double t = tom_value(L, a, ki, p.k[gj], gi == gj, p.tom_type, p.tom_denom, p.out_mode);
                 orow[gj] = t;
-                if (mirror) p.out[gj * p.n + gi] = t;
+                if (mirror && gj > gi) p.out[gj * p.n + gi] = t;
               }
             }
           }
@@ -526,29 +527,37 @@ static int build_schedule(I8Params& prm, int nkb, int w_min) {
   for (int w = 2 * (kS - 1); w >= w_min; --w) {
     int in_pass = 0;
     bool open = false;
-    for (int s = kS - 1; s >= 0; --s) {
-      int t = w - s;
+    // pairs of one weight as mirror couples (s,t),(t,s): a pass that holds whole couples has a symmetric
+    // accumulator, so L_ij and L_ji round identically; a new pass is opened before a couple that would
+    // not fit (possible while 2 * nkb <= 1023, i.e. n <= 65408)
+    for (int s = kS - 1; 2 * s >= w; --s) {
+      const int t = w - s;
       if (t < 0 || t >= kS) continue;
-      int kb = 0;
-      while (kb < nkb) {
-        if (!open || in_pass == kMaxKbPerPass) {
-          if (npass == kMaxPasses) return -1;
-          prm.pass_w[npass] = ldexp(1.0, 8 * (w - w_min));
-          ++npass;
-          in_pass = 0;
-          open = true;
+      const int members = (s == t) ? 1 : 2;
+      if (open && in_pass + members * nkb > kMaxKbPerPass && members * nkb <= kMaxKbPerPass) open = false;
+      for (int mem = 0; mem < members; ++mem) {
+        const int ps = mem == 0 ? s : t, pt = mem == 0 ? t : s;
+        int kb = 0;
+        while (kb < nkb) {
+          if (!open || in_pass == kMaxKbPerPass) {
+            if (npass == kMaxPasses) return -1;
+            prm.pass_w[npass] = ldexp(1.0, 8 * (w - w_min));
+            ++npass;
+            in_pass = 0;
+            open = true;
+          }
+          int take = nkb - kb;
+          if (take > kMaxKbPerPass - in_pass) take = kMaxKbPerPass - in_pass;
+          if (nseg == kMaxSegs) return -1;
+          prm.seg[nseg].s = (int16_t)ps;
+          prm.seg[nseg].t = (int16_t)pt;
+          prm.seg[nseg].kb0 = kb;
+          prm.seg[nseg].kb1 = kb + take;
+          prm.seg[nseg].pass = npass - 1;
+          ++nseg;
+          kb += take;
+          in_pass += take;
         }
-        int take = nkb - kb;
-        if (take > kMaxKbPerPass - in_pass) take = kMaxKbPerPass - in_pass;
-        if (nseg == kMaxSegs) return -1;
-        prm.seg[nseg].s = (int16_t)s;
-        prm.seg[nseg].t = (int16_t)t;
-        prm.seg[nseg].kb0 = kb;
-        prm.seg[nseg].kb1 = kb + take;
-        prm.seg[nseg].pass = npass - 1;
-        ++nseg;
-        kb += take;
-        in_pass += take;
       }
     }
   }
