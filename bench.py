@@ -40,6 +40,8 @@ WORKLOADS = {
     "tiny": (60, 1500, 6, 7, "signed hybrid", "signed", list(range(1, 21))),
 }
 METRIC = "TOMsimilarity+softThreshold TFLOP/s (sweep + adjacency + TOM, algorithmic flops)"
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from `ncu --set full` (profiles/), per launch
+TRAFFIC = {}
 
 
 def step_flops(m, n, P):
@@ -64,49 +66,77 @@ def parse():
 # clocks sampling (B200_PROFILING.md clocks line)
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region.  NVML is read in-process from a thread
+    (tens of microseconds per sample); `nvidia-smi -lms` in a subprocess -- the recipe's clocks line -- was
+    measured to stretch a 68 ms step to 150-420 ms on this box, so it is only the fallback."""
 
-    def __init__(self, gpu_index: int):
-        self.idx = gpu_index
-        self.proc = None
-        self.lines = []
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, gpu_index: int, uuid: str | None = None, period: float = 0.02):
+        self.idx, self.uuid, self.period = gpu_index, uuid, period
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.how = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+            import pynvml
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.time(), line.strip()))
+            pynvml.nvmlInit()
+            h = None
+            if self.uuid:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + self.uuid) if not self.uuid.startswith("GPU-") else self.uuid)
+                except Exception:
+                    h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def loop():
+                while not self.stop_flag.is_set():
+                    try:
+                        mhz = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                        rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        self.samples.append((time.time(), float(mhz), int(rs)))
+                    except Exception:
+                        pass
+                    self.stop_flag.wait(self.period)
+
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            self.how = "nvml"
+        except Exception:
+            self.how = None
 
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [l for (t, l) in self.lines if t0 - 0.05 <= t <= t1 + 0.15] or [l for _, l in self.lines]
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in rows:
-            f = [x.strip() for x in l.split(",")]
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except Exception:
-                continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
+        self.stop_flag.set()
+        if self.thread is not None:
+            self.thread.join(timeout=1.0)
+        if self.how is None or not self.samples:
+            return self._smi_once()
+        rows = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples
+        reasons = set()
+        for _, _, rs in rows:
+            for bit, nm in self.REASONS.items():
+                if rs & bit:
                     reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(reasons), "samples": len(rows), "how": "nvml thread, 20 ms period"}
+
+    def _smi_once(self):
+        try:
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+                "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.idx)],
+                                 capture_output=True, text=True, timeout=20).stdout.strip().split(",")
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            reasons = [n for n, v in zip(names, out[2:6]) if v.strip().lower().startswith("active")]
+            return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "reasons": reasons, "samples": 1,
+                    "how": "nvidia-smi once, right after the timed region (NVML unavailable)"}
+        except Exception:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "samples": 0}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -219,7 +249,8 @@ def run_ours(args):
     state = {}
 
     def step():
-        flush.zero_()  # L2 flush between steps (256 MiB > 126 MB L2); the big operands exceed L2 anyway
+        if not os.environ.get("B200W_BENCH_NOFLUSH"):
+            flush.zero_()  # L2 flush between steps (256 MiB > 126 MB L2); the big operands exceed L2 anyway
         net_dev.standardize()
         k = net_dev.sweep(powers)  # [P, n] on device
         k_host = k.cpu().numpy()  # D2H of the connectivities (P * n * 8 bytes)
@@ -249,10 +280,13 @@ def run_ours(args):
         step()
     barrier()
     tom_events.clear()
-    sampler = ClockSampler(local)
-    if rank == 0:
+    try:
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local, uuid)
+    if rank == 0 and not os.environ.get("B200W_BENCH_NOSAMPLER"):
         sampler.start()
-        time.sleep(0.3)
     launches0 = lib.b200w_launch_count()
     barrier()
     t_wall0 = time.time()
@@ -273,25 +307,28 @@ def run_ours(args):
     tom_ms = float(np.mean([a.elapsed_time(b) for a, b in tom_events]))
 
     # dominant kernel alone (the A.A contraction + TOM epilogue): CUDA events on the launching stream
-    op = net_dev._operand()
-    st = torch.cuda.current_stream().cuda_stream
-    A_rows = net_dev.A[:net_dev.nrows]
+    from pywgcna_b200.shard import symmetric_tile_count
+
     kern_ms = []
-    tt, td = L.TOM_TYPES.index(tom_type), 0
     for i in range(2 + min(args.steps, 5)):
         flush.zero_()
+        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        L.check(lib.b200w_dev_tom_compute(A_rows.data_ptr(), op.data_ptr(), net_dev.op_rows,
-                                          net_dev._scale.data_ptr(), net_dev._k.data_ptr(), n, net_dev.row0,
-                                          net_dev.nrows, tt, td, L.OUT_TOM, net_dev.prec, net_dev.T.data_ptr(),
-                                          local, st))
+        net_dev.tom_compute(TOMType=tom_type, TOMDenom="min")
         e1.record()
         torch.cuda.synchronize()
         if i >= 2:
             kern_ms.append(e0.elapsed_time(e1))
+    barrier()
     kern = float(np.mean(kern_ms))
-    kern_flops = 2.0 * net_dev.nrows * n * n  # this rank's share of 2 n^3
+    eff_flops = 2.0 * net_dev.nrows * n * n  # this rank's share of the algorithmic 2 n^3
+    if prec_name == "i8" and (world == 1 or net_dev.fused):
+        # symmetric schedule: only tiles on/above the diagonal are executed (256 x 256 x ldn MACs each)
+        tiles = symmetric_tile_count(n, world, rank, net_dev.per)
+        kern_flops = 2.0 * tiles * 256 * 256 * net_dev.ldn
+    else:
+        kern_flops = eff_flops
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -308,8 +345,13 @@ def run_ours(args):
         peak = 37.0
         peak_note = "FP64 DMMA nominal 37 TFLOP/s (HGX B200 spec; MEASURED_PEAKS.json has no f64 figure)"
     roofline = {"bound": "tensor", "achieved": kern_flops / kern / 1e9, "peak": peak, "unit": "TFLOP/s",
-                "frac": kern_flops / kern / 1e9 / peak, "traffic": None, "kernel": f"tom_compute[{prec_name}]",
-                "kernel_ms": kern, "share_of_step": kern / ms_step, "peak_note": peak_note}
+                "frac": kern_flops / kern / 1e9 / peak, "traffic": TRAFFIC.get((args.workload, prec_name, world)),
+                "kernel": f"tom_compute[{prec_name}]", "kernel_ms": kern, "share_of_step": kern / ms_step,
+                "executed_flops": kern_flops, "algorithmic_flops": eff_flops,
+                "effective": eff_flops / kern / 1e9,
+                "note": "achieved = EXECUTED flops / time (symmetric schedule: tiles on and above the diagonal "
+                        "only, mirrored by the epilogue); effective = algorithmic 2 n^3 share / time",
+                "peak_note": peak_note}
 
     # end to end through the public drop-in API (host buffers in, host buffers out)
     e2e = None

@@ -165,6 +165,28 @@ int b200w_dev_tom_compute(const double* dA_rows /* nrows x n, original */, const
                           int64_t nrows, int tom_type, int tom_denom, int out_mode, int precision,
                           double* d_out /* nrows x n */, int device, void* stream);
 
+/* Step (3) for several GPUs, symmetric and fused with its exchange.  TOM is symmetric, so only the
+ * tiles on and above the diagonal are computed, dealt out over the `world` ranks; rank r owns the
+ * output rows [r * per, (r + 1) * per) (per % 256 == 0) in ITS buffer peer_out[r] (per x n doubles).
+ * Every tile's direct half is stored into the local block, its mirrored half straight into the block of
+ * the rank that owns those rows: peer_out[q] for q != rank are PEER-MAPPED pointers (b200w_ipc_open),
+ * so the stores cross NVLink from inside the tcgen05 kernel -- no separate collective.  A rank's block
+ * is complete once every rank's call has finished (stream-order a collective, or synchronise, after it).
+ * int8 precision only.  dA_rows = this rank's rows of the original adjacency. */
+int b200w_dev_tom_compute_dist(const double* dA_rows, const void* d_operand, int64_t op_rows,
+                               const double* d_scale, const double* d_k, int64_t n, int world, int rank,
+                               int64_t per, int tom_type, int tom_denom, int out_mode,
+                               void* const* peer_out /* host array of `world` device pointers */,
+                               int device, void* stream);
+
+/* Device buffers that can be shared between the per-GPU processes of one node (plain cudaMalloc, hence
+ * exportable), and the CUDA IPC plumbing for them.  handle = 64 bytes (cudaIpcMemHandle_t). */
+int b200w_dev_malloc(int64_t bytes, int device, void** out);
+int b200w_dev_free(void* p, int device);
+int b200w_ipc_export(void* p, unsigned char* handle64);
+int b200w_ipc_open(const unsigned char* handle64, int device, void** out);
+int b200w_ipc_close(void* p, int device);
+
 /* ----------------------------------------------------------------------- introspection */
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t b200w_launch_count(void);

@@ -60,6 +60,13 @@ SIGNATURES = {
     "b200w_dev_tom_prepare": (_int, [_dp, _i64, _i64, _i64, _int, _dp, _i64, _dp, _dp, _int, _dp]),
     "b200w_dev_tom_compute": (_int, [_dp, _dp, _i64, _dp, _dp, _i64, _i64, _i64, _int, _int, _int, _int,
                                      _dp, _int, _dp]),
+    "b200w_dev_tom_compute_dist": (_int, [_dp, _dp, _i64, _dp, _dp, _i64, _int, _int, _i64, _int, _int, _int,
+                                          C.POINTER(C.c_void_p), _int, _dp]),
+    "b200w_dev_malloc": (_int, [_i64, _int, C.POINTER(C.c_void_p)]),
+    "b200w_dev_free": (_int, [_dp, _int]),
+    "b200w_ipc_export": (_int, [_dp, C.c_char_p]),
+    "b200w_ipc_open": (_int, [C.c_char_p, _int, C.POINTER(C.c_void_p)]),
+    "b200w_ipc_close": (_int, [_dp, _int]),
     "b200w_launch_count": (_i64, []),
     "b200w_last_kernel_ms": (_dbl, []),
 }

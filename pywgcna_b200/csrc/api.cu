@@ -177,6 +177,39 @@ static HostPool g_pool;
 
 using namespace b200w;
 
+extern "C" int b200w_dev_malloc(int64_t bytes, int device, void** out) {
+  if (!out || bytes < 0) return fail(B200W_E_INVALID, "dev_malloc: bad args");
+  if (int e = ensure_device(device)) return e;
+  B200W_CUDA(cudaMalloc(out, bytes ? (size_t)bytes : 16));
+  return 0;
+}
+extern "C" int b200w_dev_free(void* p, int device) {
+  if (int e = ensure_device(device)) return e;
+  B200W_CUDA(cudaFree(p));
+  return 0;
+}
+extern "C" int b200w_ipc_export(void* p, unsigned char* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  if (!p || !handle64) return fail(B200W_E_INVALID, "ipc_export: bad args");
+  cudaIpcMemHandle_t h;
+  B200W_CUDA(cudaIpcGetMemHandle(&h, p));
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+extern "C" int b200w_ipc_open(const unsigned char* handle64, int device, void** out) {
+  if (!handle64 || !out) return fail(B200W_E_INVALID, "ipc_open: bad args");
+  if (int e = ensure_device(device)) return e;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  B200W_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+extern "C" int b200w_ipc_close(void* p, int device) {
+  if (int e = ensure_device(device)) return e;
+  B200W_CUDA(cudaIpcCloseMemHandle(p));
+  return 0;
+}
+
 extern "C" void* b200w_host_alloc(int64_t bytes) { return bytes < 0 ? nullptr : g_pool.alloc((size_t)bytes); }
 extern "C" void b200w_host_free(void* p) { g_pool.free(p); }
 extern "C" void b200w_host_trim(void) { g_pool.trim(); }

@@ -207,7 +207,8 @@ int b200w_tom_prepare_i8(const double* dA_rows, int64_t n, int64_t row0, int64_t
 int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t op_rows,
                          const double* d_scale,
                          const double* d_k, int64_t n, int64_t row0, int64_t nrows, int tom_type,
-                         int tom_denom, int out_mode, double* d_out, cudaStream_t st);
+                         int tom_denom, int out_mode, double* d_out, cudaStream_t st, int world,
+                         int rank, int64_t per, double* const* peer_out);
 
 int b200w::resolve_precision(int precision) {
   if (precision == B200W_PREC_AUTO) return B200W_PREC_I8;
@@ -267,9 +268,32 @@ extern "C" int b200w_dev_tom_compute(const double* dA_rows, const void* d_operan
   if (precision == B200W_PREC_I8) {
     if (!d_scale) return fail(B200W_E_INVALID, "tom_compute: i8 needs d_scale");
     return b200w_tom_compute_i8(dA_rows, d_operand, op_rows, d_scale, d_k, n, row0, nrows, tom_type,
-                                tom_denom, out_mode, d_out, st);
+                                tom_denom, out_mode, d_out, st, 1, 0, 0, nullptr);
   }
   return fail(B200W_E_INVALID, "tom_compute: unknown precision %d", precision);
+}
+
+extern "C" int b200w_dev_tom_compute_dist(const double* dA_rows, const void* d_operand,
+                                          int64_t op_rows, const double* d_scale, const double* d_k,
+                                          int64_t n, int world, int rank, int64_t per, int tom_type,
+                                          int tom_denom, int out_mode, void* const* peer_out,
+                                          int device, void* stream) {
+  if (!dA_rows || !d_operand || !d_scale || !d_k || !peer_out || n < 1 || world < 1 || world > 8 ||
+      rank < 0 || rank >= world || per < 256 || per % 256)
+    return fail(B200W_E_INVALID, "tom_compute_dist: bad args");
+  if (tom_type < 0 || tom_type > 1 || tom_denom < 0 || tom_denom > 1 || out_mode < 0 || out_mode > 2)
+    return fail(B200W_E_INVALID, "tom_compute_dist: bad enum");
+  if (op_rows < round_up(n, 128) || op_rows % 128)
+    return fail(B200W_E_INVALID, "tom_compute_dist: op_rows must be a multiple of 128 >= n");
+  const int64_t row0 = (int64_t)rank * per;
+  if (row0 >= n) return 0;  // a trailing rank without rows
+  const int64_t nrows = (row0 + per <= n ? per : n - row0);
+  if (int e = ensure_device(device)) return e;
+  for (int r = 0; r < world; ++r)
+    if (!peer_out[r] && (int64_t)r * per < n) return fail(B200W_E_INVALID, "tom_compute_dist: peer_out[%d] is NULL", r);
+  return b200w_tom_compute_i8(dA_rows, d_operand, op_rows, d_scale, d_k, n, row0, nrows, tom_type,
+                              tom_denom, out_mode, (double*)peer_out[rank], (cudaStream_t)stream, world,
+                              rank, per, (double* const*)peer_out);
 }
 
 int b200w_dev_intramodular(const double* dA, int64_t n, const int32_t* d_labels,

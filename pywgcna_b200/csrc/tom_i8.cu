@@ -24,6 +24,7 @@
 //            scratch (coalesced: lanes = rows), last pass applies (L + a) / (min(k_i,k_j) + 1 - a)
 #include <cuda.h>
 
+#include <algorithm>
 #include <map>
 #include <vector>
 
@@ -54,7 +55,10 @@ struct I8Params {
   int32_t tiles_m, tiles_n;
   const int2* tile_list;  // (tm, tn) per tile, in an order that keeps co-resident tiles on shared panels
   int32_t n_tiles;
-  int32_t symmetric;      // only tiles tn >= tm are listed; off-diagonal tiles are also stored mirrored
+  int32_t symmetric;      // every listed off-diagonal tile is also stored mirrored (TOM_ji := TOM_ij)
+  int64_t tile_row_base;  // tile row index tm counts 256/128-row tiles from this row (row0, or 0 for global lists)
+  int64_t per_rows;       // rows per rank: the mirrored entry (gj, gi) belongs to rank gj / per_rows ...
+  double* peer_out[8];    // ... and is stored into that rank's row block (peer HBM over NVLink)
   int32_t nseg, npass;
   int32_t tom_type, tom_denom, out_mode, group;
   int32_t sync_mode;       // 0 none, 1 grid barrier of the producers per tile, 2 per segment
@@ -340,7 +344,7 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
           tm = t2.x;
           tn = t2.y;
         }
-        const int i0 = (int)(p.row0 + tm * Cfg::kTileRows + rank * kTM), j0 = (int)(tn * kTN);
+        const int i0 = (int)(p.tile_row_base + tm * Cfg::kTileRows + rank * kTM), j0 = (int)(tn * kTN);
         for (int sg = 0; sg < p.nseg; ++sg) {
           const Seg sgm = p.seg[sg];
           if (p.sync_mode == 2 || (p.sync_mode == 1 && sg == 0)) {
@@ -437,11 +441,13 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
       if (tile >= n_tiles) break;
       const int2 t2 = p.tile_list[tile];
       const int64_t tm = t2.x, tn = t2.y;
-      const int64_t gi = p.row0 + tm * Cfg::kTileRows + rank * kTM + row, j0 = tn * kTN;
+      const int64_t gi = p.tile_row_base + tm * Cfg::kTileRows + rank * kTM + row, j0 = tn * kTN;
       // symmetric schedule: TOM_ji = TOM_ij, stored from the same registers; for a fixed column the 32
       // lanes of a warp hold 32 consecutive rows, so the mirrored store is one coalesced 256-byte line
-      // (in a diagonal tile only the entries on and above the diagonal are stored, with their mirror)
+      // (in a diagonal tile only the entries on and above the diagonal are stored, with their mirror);
+      // the mirrored row gj may belong to another GPU: the store then goes to that GPU's HBM
       const bool mirror = p.symmetric != 0;
+      const bool diag_tile = p.tile_row_base + tm * Cfg::kTileRows == tn * kTN;
       const bool row_ok = gi < p.row0 + p.nrows;
       const double ki = row_ok ? p.k[gi] : 0.0;
       const double si = row_ok ? p.scale[gi] * p.final_scale : 0.0;
@@ -470,12 +476,15 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
               double v = (double)(int)r[col] * w;
               if (!first) v += sc[col * kTM];
               const int64_t gj = j0 + c * 32 + col;
-              if (row_ok && gj < p.n && !(mirror && gj < gi)) {
+              if (row_ok && gj < p.n && !(mirror && diag_tile && gj < gi)) {
                 const double L = v * (si * p.scale[gj]);
                 const double a = tom_clean(arow[gj], gi, gj);
                 const double t = tom_value(L, a, ki, p.k[gj], gi == gj, p.tom_type, p.tom_denom, p.out_mode);
                 orow[gj] = t;
-                if (mirror && gj > gi) p.out[gj * p.n + gi] = t;
+                if (mirror && !(diag_tile && gj <= gi)) {
+                  const int64_t owner = gj / p.per_rows;
+                  p.peer_out[owner][(gj - owner * p.per_rows) * p.n + gi] = t;
+                }
               }
             }
           }
@@ -582,7 +591,8 @@ int b200w_tom_prepare_i8(const double* dA_rows, int64_t n, int64_t row0, int64_t
 
 int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t op_rows, const double* d_scale,
                          const double* d_k, int64_t n, int64_t row0, int64_t nrows, int tom_type, int tom_denom,
-                         int out_mode, double* d_out, cudaStream_t st) {
+                         int out_mode, double* d_out, cudaStream_t st, int world, int rank, int64_t per,
+                         double* const* peer_out) {
   const int64_t ldn = b200w_padded_n(n);
   if (op_rows > 0x7fffffff || ldn > 0x7fffffff) return fail(B200W_E_UNSUPPORTED, "tom_i8: n too large");
   EncodeTiledFn encode = get_encode_tiled();
@@ -629,17 +639,47 @@ int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t o
   // 1e-12), so only the tiles on and above the diagonal are computed and mirrored -- half the MMAs.
   // The list is ordered in square super-blocks of G x G tiles so that the ~74 co-resident tiles touch
   // ~2G distinct operand panels.
-  bool symmetric = (ctas == 2) && row0 == 0 && nrows == n;
-  if (const char* e = getenv("B200W_I8_SYMMETRIC")) symmetric = symmetric && atoi(e) != 0;
-  // the list depends only on (device, TM, TN, G, symmetric): built and uploaded once, then cached
+  // Several GPUs (world > 1, peer_out given): the upper triangle of 256 x 256 tiles is dealt out over
+  // the ranks -- tile {a, b}, a < b, goes to the owner of row tile a if a + b is even, else to the owner
+  // of row tile b, oriented so that its direct rows are the rank's own; the mirrored half is stored
+  // straight into the owning peer's row block (coalesced 256-byte lines over NVLink).
+  const bool dist = world > 1 && peer_out != nullptr && ctas == 2;
+  if (world > 8) return fail(B200W_E_UNSUPPORTED, "tom_i8: at most 8 ranks");
+  if (dist && (per % 256 != 0 || row0 != rank * per))
+    return fail(B200W_E_INVALID, "tom_i8: distributed mode needs per %% 256 == 0 and row0 == rank * per");
+  bool symmetric = (ctas == 2) && ((row0 == 0 && nrows == n) || dist);
+  if (const char* e = getenv("B200W_I8_SYMMETRIC")) symmetric = symmetric && (atoi(e) != 0 || dist);
+  prm.tile_row_base = dist ? 0 : row0;
+  prm.per_rows = dist ? per : op_rows;
+  for (int r = 0; r < 8; ++r) prm.peer_out[r] = dist && r < world ? peer_out[r] : d_out;
+  // the list depends only on (device, TM, TN, G, symmetric, world, rank, per): built once, then cached
   static std::map<std::vector<int>, std::pair<int2*, int>> tile_cache;
-  const std::vector<int> key = {dev, prm.tiles_m, prm.tiles_n, prm.group, symmetric ? 1 : 0};
+  const std::vector<int> key = {dev, prm.tiles_m, prm.tiles_n, prm.group, symmetric ? 1 : 0,
+                                dist ? world : 1, dist ? rank : 0, dist ? (int)(per / 256) : 0};
   auto hit = tile_cache.find(key);
   if (hit == tile_cache.end()) {
     std::vector<int2> tiles;
     const int TM = prm.tiles_m, TN = prm.tiles_n;
     int G = prm.group > 0 ? prm.group : 8;
-    if (symmetric) {
+    if (dist) {
+      const int T = TN, ptiles = (int)(per / 256);
+      auto owner = [&](int t) { return t / ptiles; };
+      for (int a = 0; a < T; ++a) {
+        if (owner(a) == rank) tiles.push_back(make_int2(a, a));
+        for (int b = a + 1; b < T; ++b) {
+          const int oa = owner(a), ob = owner(b);
+          const int o = (oa == ob) ? oa : (((a + b) & 1) == 0 ? oa : ob);
+          if (o != rank) continue;
+          tiles.push_back(oa == rank ? make_int2(a, b) : make_int2(b, a));
+        }
+      }
+      std::sort(tiles.begin(), tiles.end(), [G](const int2& x, const int2& y) {
+        const int kx[4] = {x.y / G, x.x / G, x.y, x.x}, ky[4] = {y.y / G, y.x / G, y.y, y.x};
+        for (int i = 0; i < 4; ++i)
+          if (kx[i] != ky[i]) return kx[i] < ky[i];
+        return false;
+      });
+    } else if (symmetric) {
       for (int bn = 0; bn * G < TN; ++bn)
         for (int bm = 0; bm <= bn; ++bm)
           for (int tn = bn * G; tn < TN && tn < (bn + 1) * G; ++tn)

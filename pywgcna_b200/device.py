@@ -1,15 +1,24 @@
-"""Device-resident chaining of the hot path and its row-block sharding over
-several GPUs.  PyTorch is used for device memory, streams and ``torch.distributed``
-only; every kernel launched here is one of libb200wgcna's, through the dev_* entry points of
-``include/b200wgcna.h``.
+"""Device-resident chaining of the hot path and its sharding over several GPUs
+(SURVEY 8e).  PyTorch is used for device memory, streams and ``torch.distributed`` only; every kernel
+launched here is one of libb200wgcna's, through the dev_* entry points of ``include/b200wgcna.h``.
 
 Single GPU:   DeviceNetwork(X).sweep(powers) -> k ; .adjacency(power) ; .tom() -> TOM in HBM
-Several GPUs: one process per GPU (torchrun); rank r owns the contiguous row block
-              ``row_block(n, world, r)`` of the adjacency / TOM and the same block of sweep columns.
-              Exchange steps (NCCL all-gather): k after the sweep; the TOM operand row blocks (int8
-              digit planes or FP64 rows), their scales and k before the contraction.
+Several GPUs: one process per GPU (torchrun).  Rank r owns the contiguous row block
+              ``row_block(n, world, r, 256)`` of the adjacency / TOM and the same block of sweep columns.
+  sweep       own columns, then all-gather of k (NCCL)
+  adjacency   own rows
+  TOM         own rows -> int8 digit planes; all-gather of the planes, their scales and k (NCCL, 1 byte
+              per element and plane instead of 8); then the SYMMETRIC contraction: the upper triangle of
+              256 x 256 tiles is dealt out over the ranks and every tile's mirrored half is stored by the
+              tcgen05 kernel itself into the owning peer's row block over NVLink (CUDA-IPC mapped
+              buffers) -- compute and exchange in one kernel.  ``tom_finish()`` stream-orders a tiny
+              all-reduce after it, which is the point where every rank's block is complete.
+              ``B200WGCNA_DIST=rowblock`` selects the plain row-block contraction (no peer stores).
 """
 from __future__ import annotations
+
+import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -17,12 +26,22 @@ import torch
 from . import _lib as L
 from .shard import all_gather_rows, row_block, rows_per_rank
 
+ALIGN = 256  # row blocks start on 256-row tile boundaries (the CTA-pair tile of the int8 kernel)
+
+
+class _DevView:
+    """__cuda_array_interface__ over a raw device pointer, so torch can view library-owned memory."""
+
+    def __init__(self, ptr: int, shape, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
 
 class DeviceNetwork:
     """Expression matrix resident in HBM; sweep / adjacency / TOM without leaving the device."""
 
     def __init__(self, X, device: int = 0, networkType: str = "unsigned", group=None, world: int | None = None,
-                 rank: int | None = None, precision: str = "auto"):
+                 rank: int | None = None, precision: str = "auto", use_dist: bool | None = None):
         self.lib = L.load()
         self.device = int(device)
         torch.cuda.set_device(self.device)
@@ -30,13 +49,18 @@ class DeviceNetwork:
         self.net = L.NET_TYPES.index(networkType)
         self.prec = {"auto": L.PREC_AUTO, "f64": L.PREC_F64, "i8": L.PREC_I8}[precision]
         self.group = group
+        self.use_dist = use_dist  # torch.distributed collectives (False: the caller moves the blocks, tests)
         if world is None:
             if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
                 import torch.distributed as dist
 
                 world, rank = dist.get_world_size(group), dist.get_rank(group)
+                if self.use_dist is None:
+                    self.use_dist = True
             else:
                 world, rank = 1, 0
+        elif self.use_dist is None:
+            self.use_dist = torch.distributed.is_available() and torch.distributed.is_initialized()
         self.world, self.rank = int(world), int(rank)
         if isinstance(X, torch.Tensor):
             self.X = X.to(self.dev, torch.float64).contiguous()
@@ -47,13 +71,29 @@ class DeviceNetwork:
         self.ldn = self.lib.b200w_padded_n(self.n)
         self.Z = torch.empty((self.n, self.ldk), dtype=torch.float64, device=self.dev)
         self.bad = torch.empty(self.n, dtype=torch.uint8, device=self.dev)
-        self.per = rows_per_rank(self.n, self.world)
-        self.row0, self.nrows = row_block(self.n, self.world, self.rank)
+        self.per = rows_per_rank(self.n, self.world, ALIGN)
+        self.row0, self.nrows = row_block(self.n, self.world, self.rank, ALIGN)
         self.op_rows = self.per * self.world  # >= round_up(n, 128); equal blocks for the all-gather
+        elt = self.lib.b200w_tom_operand_bytes(128, self.prec) // (128 * 128)  # bytes per element over all planes
+        self.planes, self.elt = (1, 8) if elt == 8 else (elt, 1)
+        self.fused = (self.world > 1 and self.elt == 1
+                      and os.environ.get("B200WGCNA_DIST", "fused") != "rowblock")
         self.A = None
         self.T = None
+        self._T_raw = None
+        self._peer_ptrs = None
+        self._peer_open = []
         self._op = None
         self._standardized = False
+
+    def __del__(self):
+        try:
+            for p in self._peer_open:
+                self.lib.b200w_ipc_close(p, self.device)
+            if self._T_raw:
+                self.lib.b200w_dev_free(self._T_raw, self.device)
+        except Exception:
+            pass
 
     def _stream(self):
         return torch.cuda.current_stream(self.dev).cuda_stream
@@ -65,9 +105,10 @@ class DeviceNetwork:
 
     def _all_gather_rows(self, full: torch.Tensor):
         """In-place all-gather of the ``per``-row blocks of ``full`` ([op_rows, ...], contiguous)."""
-        all_gather_rows(full, self.per, self.rank, self.world, self.group)
+        if self.use_dist:
+            all_gather_rows(full, self.per, self.rank, self.world, self.group)
 
-    # -- the three stages ------------------------------------------------------------------
+    # -- sweep and adjacency -------------------------------------------------------------------
     def sweep(self, powers) -> torch.Tensor:
         """k[P, n] (device, replicated on every rank) for the ascending power vector
         (wgcna.py:873-920)."""
@@ -102,36 +143,106 @@ class DeviceNetwork:
                                                  self.device, self._stream()))
         return self.A[:self.nrows]
 
+    # -- TOM -----------------------------------------------------------------------------------
     def _operand(self):
         if self._op is None:
-            elt = self.lib.b200w_tom_operand_bytes(128, self.prec) // (128 * 128)  # bytes / element / all planes
-            self.planes, self.elt = (1, 8) if elt == 8 else (elt, 1)
             self._op = torch.zeros((self.planes, self.op_rows, self.ldn * self.elt), dtype=torch.uint8, device=self.dev)
             self._scale = torch.zeros(self.op_rows, dtype=torch.float64, device=self.dev)
             self._k = torch.zeros(self.op_rows, dtype=torch.float64, device=self.dev)
         return self._op
 
+    def _out(self):
+        """This rank's TOM row block.  In the fused multi-GPU mode it lives in a cudaMalloc buffer of
+        ``per`` rows that the peers map through CUDA IPC."""
+        if self.T is None:
+            rows = self.per if self.fused else max(self.nrows, 1)
+            if self.fused:
+                p = C.c_void_p()
+                L.check(self.lib.b200w_dev_malloc(rows * self.n * 8, self.device, C.byref(p)))
+                self._T_raw = p.value
+                self.T = torch.as_tensor(_DevView(p.value, (rows, self.n)), device=self.dev)
+            else:
+                self.T = torch.empty((rows, self.n), dtype=torch.float64, device=self.dev)
+        return self.T
+
+    def ipc_handle(self) -> bytes:
+        self._out()
+        h = C.create_string_buffer(64)
+        L.check(self.lib.b200w_ipc_export(self._T_raw, h))
+        return h.raw
+
+    def connect_peers(self, ptrs=None):
+        """Table of every rank's TOM block as seen from this GPU.  ``ptrs`` (tests: ranks emulated in one
+        process) are used as they are; otherwise CUDA IPC handles are exchanged over the process group."""
+        self._out()
+        if ptrs is None:
+            import torch.distributed as dist
+
+            mine = torch.frombuffer(bytearray(self.ipc_handle()), dtype=torch.uint8).to(self.dev)
+            allh = torch.zeros((self.world, 64), dtype=torch.uint8, device=self.dev)
+            dist.all_gather_into_tensor(allh, mine, group=self.group)
+            allh = allh.cpu().numpy()
+            ptrs = []
+            for r in range(self.world):
+                if r == self.rank:
+                    ptrs.append(self._T_raw)
+                else:
+                    p = C.c_void_p()
+                    L.check(self.lib.b200w_ipc_open(allh[r].tobytes(), self.device, C.byref(p)))
+                    self._peer_open.append(p.value)
+                    ptrs.append(p.value)
+        self._peer_ptrs = (C.c_void_p * self.world)(*[int(p) for p in ptrs])
+
+    def tom_prepare(self, A_rows: torch.Tensor | None = None):
+        A_rows = self.A[:self.nrows] if A_rows is None else A_rows
+        op = self._operand()
+        self._A_rows = A_rows
+        if self.nrows > 0:
+            L.check(self.lib.b200w_dev_tom_prepare(A_rows.data_ptr(), self.n, self.row0, self.nrows, self.prec,
+                                                   op.data_ptr(), self.op_rows, self._scale.data_ptr(),
+                                                   self._k.data_ptr(), self.device, self._stream()))
+
+    def tom_exchange(self):
+        if self.world > 1:
+            for p in range(self.planes):
+                self._all_gather_rows(self._op[p])
+            self._all_gather_rows(self._k)
+            self._all_gather_rows(self._scale)
+
+    def tom_compute(self, TOMType: str = "signed", TOMDenom: str = "min", out_mode: int = L.OUT_TOM):
+        tt, td = L.TOM_TYPES.index(TOMType), L.TOM_DENOMS.index(TOMDenom)
+        T = self._out()
+        if self.nrows == 0:
+            return T[:0]
+        if self.fused:
+            if self._peer_ptrs is None:
+                self.connect_peers()
+            L.check(self.lib.b200w_dev_tom_compute_dist(self._A_rows.data_ptr(), self._op.data_ptr(), self.op_rows,
+                                                        self._scale.data_ptr(), self._k.data_ptr(), self.n,
+                                                        self.world, self.rank, self.per, tt, td, out_mode,
+                                                        self._peer_ptrs, self.device, self._stream()))
+        else:
+            L.check(self.lib.b200w_dev_tom_compute(self._A_rows.data_ptr(), self._op.data_ptr(), self.op_rows,
+                                                   self._scale.data_ptr(), self._k.data_ptr(), self.n, self.row0,
+                                                   self.nrows, tt, td, out_mode, self.prec, T.data_ptr(),
+                                                   self.device, self._stream()))
+        return T[:self.nrows]
+
+    def tom_finish(self):
+        """Fused multi-GPU mode: peers store into this rank's block, so it is complete only when every
+        rank's kernel has finished -- a one-element all-reduce on the stream orders exactly that."""
+        if self.fused and self.use_dist:
+            import torch.distributed as dist
+
+            if not hasattr(self, "_flag"):
+                self._flag = torch.zeros(1, dtype=torch.float32, device=self.dev)
+            dist.all_reduce(self._flag, group=self.group)
+
     def tom(self, TOMType: str = "signed", TOMDenom: str = "min", out_mode: int = L.OUT_TOM,
             A_rows: torch.Tensor | None = None) -> torch.Tensor:
         """This rank's row block of the TOM (wgcna.py:1141-1157) from its adjacency row block."""
-        tt, td = L.TOM_TYPES.index(TOMType), L.TOM_DENOMS.index(TOMDenom)
-        A_rows = self.A[:self.nrows] if A_rows is None else A_rows
-        n = self.n
-        op = self._operand()
-        if self.T is None:
-            self.T = torch.empty((max(self.nrows, 1), n), dtype=torch.float64, device=self.dev)
-        if self.nrows > 0:
-            L.check(self.lib.b200w_dev_tom_prepare(A_rows.data_ptr(), n, self.row0, self.nrows, self.prec,
-                                                   op.data_ptr(), self.op_rows, self._scale.data_ptr(),
-                                                   self._k.data_ptr(), self.device, self._stream()))
-        if self.world > 1:
-            for p in range(self.planes):
-                self._all_gather_rows(op[p])
-            self._all_gather_rows(self._k)
-            self._all_gather_rows(self._scale)
-        if self.nrows > 0:
-            L.check(self.lib.b200w_dev_tom_compute(A_rows.data_ptr(), op.data_ptr(), self.op_rows,
-                                                   self._scale.data_ptr(), self._k.data_ptr(), n, self.row0,
-                                                   self.nrows, tt, td, out_mode, self.prec, self.T.data_ptr(),
-                                                   self.device, self._stream()))
-        return self.T[:self.nrows]
+        self.tom_prepare(A_rows)
+        self.tom_exchange()
+        T = self.tom_compute(TOMType, TOMDenom, out_mode)
+        self.tom_finish()
+        return T

@@ -28,6 +28,25 @@ def padded_rows(n: int, world: int, align: int = 128) -> int:
     return rows_per_rank(n, world, align) * world
 
 
+def symmetric_tile_count(n: int, world: int = 1, rank: int = 0, per: int | None = None, tile: int = 256) -> int:
+    """Number of 256 x 256 tiles the symmetric int8 TOM schedule gives to ``rank`` (same deal as
+    b200w_tom_compute_i8: diagonal tiles to their owner, tile {a, b} to the owner of a if a + b is even,
+    else to the owner of b).  world == 1: the whole upper triangle, T (T + 1) / 2."""
+    T = -(-n // tile)
+    if world == 1:
+        return T * (T + 1) // 2
+    ptiles = per // tile
+    cnt = 0
+    for a in range(T):
+        oa = a // ptiles
+        cnt += oa == rank
+        for b in range(a + 1, T):
+            ob = b // ptiles
+            o = oa if oa == ob else (oa if (a + b) % 2 == 0 else ob)
+            cnt += o == rank
+    return cnt
+
+
 def all_gather_rows(full: torch.Tensor, per: int, rank: int, world: int, group=None) -> None:
     """In-place all-gather: ``full`` is [per * world, ...] contiguous and rank r has filled rows
     ``[r * per, (r + 1) * per)``; afterwards every rank holds every block."""

@@ -214,3 +214,63 @@ def test_properties_at_scale(gpu, prec):
         Tr = (Lr + A0[rows]) / (np.minimum(kk[rows][:, None], kk[None, :]) + 1 - A0[rows])
         Tr[np.arange(len(rows)), rows] = 1
         assert np.max(np.abs(T[rows] - Tr)) < TOL_TOM[prec]
+
+
+@pytest.mark.parametrize("world,n", [(2, 1500), (3, 1500), (4, 2100), (8, 2304)])
+def test_multi_gpu_path_emulated_on_one_gpu(gpu, world, n):
+    """The N-GPU path with its ranks emulated sequentially on one device (B200_PROFILING.md: ranks that
+    wait on one another must not run as separate launches on one GPU; these do not wait -- the exchange
+    is done by the test).  Row blocks, the digit-plane exchange layout, the distributed symmetric tile
+    deal and the mirrored stores into "peer" blocks must reproduce the single-GPU result bit for bit."""
+    import torch
+
+    from pywgcna_b200.device import DeviceNetwork
+
+    X = make_expression(60, n, F=6, seed=n + world)
+    powers = list(range(1, 13))
+    ref = DeviceNetwork(X, device=0, networkType="signed hybrid")
+    k_ref = ref.sweep(powers)
+    A_ref = ref.adjacency(6).clone()
+    T_ref = ref.tom(TOMType="signed").clone()
+
+    nets = [DeviceNetwork(X, device=0, networkType="signed hybrid", world=world, rank=r, use_dist=False)
+            for r in range(world)]
+    assert sum(net.nrows for net in nets) == n and all(net.fused for net in nets)
+    # sweep: every rank its own block of columns
+    k = torch.zeros_like(k_ref)
+    for net in nets:
+        if net.nrows:
+            steps = np.ones(len(powers))
+            kloc = torch.empty((len(powers), net.nrows), dtype=torch.float64, device="cuda")
+            net.standardize()
+            _lib.check(net.lib.b200w_dev_sweep(net.Z.data_ptr(), net.bad.data_ptr(), net.m, net.n, steps.ctypes.data,
+                                               len(powers), net.net, net.row0, net.nrows, kloc.data_ptr(), 0,
+                                               torch.cuda.current_stream().cuda_stream))
+            k[:, net.row0:net.row0 + net.nrows] = kloc
+    torch.testing.assert_close(k, k_ref, rtol=1e-12, atol=1e-12)
+    # adjacency row blocks
+    for net in nets:
+        net.adjacency(6)
+    A = torch.cat([net.A[:net.nrows] for net in nets])
+    assert torch.equal(A, A_ref)
+    # TOM: prepare, emulate the all-gather of planes / scale / k, fused symmetric compute with peer stores
+    for net in nets:
+        net.tom_prepare()
+    for dst in nets:
+        for src in nets:
+            if src is not dst and src.nrows:
+                sl = slice(src.row0, src.row0 + src.nrows)
+                dst._op[:, sl] = src._op[:, sl]
+                dst._k[sl] = src._k[sl]
+                dst._scale[sl] = src._scale[sl]
+    for net in nets:
+        net._out().fill_(float("nan"))
+    ptrs = [net._T_raw for net in nets]
+    for net in nets:
+        net.connect_peers(ptrs)
+    for net in nets:
+        net.tom_compute(TOMType="signed")
+    torch.cuda.synchronize()
+    T = torch.cat([net.T[:net.nrows] for net in nets])
+    assert not torch.isnan(T).any(), "a tile of the distributed schedule was never written"
+    assert torch.equal(T, T_ref)
