@@ -95,11 +95,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a protocol bug must end as a trapped launch, never as a hung GPU.
+// Bounded wait: a protocol bug must end as a trapped launch, never as a hung GPU.  The bound is wall
+// time (20 s on %globaltimer, checked every 4096 polls), not a poll count: under a profiler's
+// instrumented replay a legitimate wait lasts orders of magnitude longer than in a plain run.
+__device__ __forceinline__ uint64_t global_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr uint64_t kWaitLimitNs = 20ull * 1000ull * 1000ull * 1000ull;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) __trap();
+    if ((++spins & 4095u) == 0) {
+      const uint64_t now = global_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kWaitLimitNs) __trap();
+    }
   }
 }
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0,
@@ -347,19 +360,36 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
         const int i0 = (int)(p.tile_row_base + tm * Cfg::kTileRows + rank * kTM), j0 = (int)(tn * kTN);
         for (int sg = 0; sg < p.nseg; ++sg) {
           const Seg sgm = p.seg[sg];
-          if (p.sync_mode == 2 || (p.sync_mode == 1 && sg == 0)) {
+          // sync_mode 3: split barrier -- the arrival for segment g was posted kLead K-blocks before the
+          // end of segment g - 1 (below), so by the time a producer gets here most CTAs have arrived and the
+          // ring does not drain; the skew between CTAs stays below one segment + kLead stages.
+          const bool split = p.sync_mode == 3;
+          if (split && sync_seq == 0) atomicAdd(p.sync_ctr, 1u);  // arrival for the very first segment
+          if (p.sync_mode == 2 || split || (p.sync_mode == 1 && sg == 0)) {
             ++sync_seq;
-            __threadfence();
-            atomicAdd(p.sync_ctr, 1u);
+            if (!split) {
+              __threadfence();
+              atomicAdd(p.sync_ctr, 1u);
+            }
             const unsigned int target = sync_seq * gridDim.x;
             unsigned int v, spins = 0;
+            uint64_t t0 = 0;
             do {
               asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.sync_ctr) : "memory");
-              if (++spins > (1u << 24)) __trap();
+              if ((++spins & 4095u) == 0) {
+                const uint64_t now = global_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > kWaitLimitNs) __trap();
+              }
             } while (v < target);
           }
-          if (!active) continue;
+          if (!active) {
+            if (split) atomicAdd(p.sync_ctr, 1u);  // arrival for the next segment
+            continue;
+          }
+          const int arrive_kb = (sgm.kb1 - kStages > sgm.kb0) ? sgm.kb1 - kStages : sgm.kb0;
           for (int kb = sgm.kb0; kb < sgm.kb1; ++kb) {
+            if (split && kb == arrive_kb) atomicAdd(p.sync_ctr, 1u);  // arrival for the next segment
             mbar_wait(&bars->empty[stage], phase ^ 1);
             uint8_t* a_dst = smem + stage * kStageBytes;
             uint8_t* b_dst = a_dst + kTM * kKB;
@@ -704,7 +734,7 @@ int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t o
   Scratch scratch;
   B200W_CUDA(scratch.alloc((size_t)grid * kTM * kTN * sizeof(double), st));
   prm.scratch = scratch.as<double>();
-  prm.sync_mode = 2;
+  prm.sync_mode = 3;
   if (const char* e = getenv("B200W_I8_SYNC")) prm.sync_mode = atoi(e);
   Scratch ctr;
   B200W_CUDA(ctr.alloc(64, st));
@@ -730,9 +760,13 @@ int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t o
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     int na = 0;
-    attr[na].id = cudaLaunchAttributeCooperative;
-    attr[na].val.cooperative = 1;
-    ++na;
+    // (B200W_I8_NOCOOP=1 drops the attribute: Nsight Compute 2025.2 fails to replay a launch that is
+    //  both cooperative and clustered; the grid is one CTA per SM, so it is co-resident in practice)
+    if (!getenv("B200W_I8_NOCOOP")) {
+      attr[na].id = cudaLaunchAttributeCooperative;
+      attr[na].val.cooperative = 1;
+      ++na;
+    }
     if (ctas == 2) {
       attr[na].id = cudaLaunchAttributeClusterDimension;
       attr[na].val.clusterDim.x = 2;
