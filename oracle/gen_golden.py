@@ -91,6 +91,17 @@ def main():
         out[nm] = k
         out[nm + "_fit"] = R.ref_scaleFreeFitIndex(k).to_numpy(dtype=np.float64)[0]
     np.savez_compressed(os.path.join(OUT, "scale_free_fit.npz"), **out)
+    # (6) end to end through the reference's own clustering (findModules, wgcna.py:278-334): power,
+    #     adjacency, TOM, round(1 - TOM, 8), linkage(average), cutreeHybrid -> module labels
+    X = make_expression(100, 600, F=5, seed=606, grey_frac=0.25, loading=(1.5, 3.0))  # clear modules
+    df = pd.DataFrame(X)
+    p, sft = R.ref_pickSoftThreshold(df, networkType="signed hybrid", powerVector=DEFAULT_POWERS)
+    A = R.ref_adjacency(df, adjacencyType="signed hybrid", power=p)
+    T = R.ref_TOMsimilarity(A, TOMType="signed").to_numpy()
+    labels, Z = R.ref_modules_from_tom(T, minClusterSize=30)
+    np.savez_compressed(os.path.join(OUT, "e2e_modules.npz"), X=X, powers=np.asarray(DEFAULT_POWERS), power=np.int64(p),
+                        sft=sft_to_array(sft), labels=labels, linkage=Z, tom_sample=T[:8].copy())
+    print("e2e_modules: power", p, "modules", np.unique(labels, return_counts=True))
     print("wrote", sorted(os.listdir(OUT)))
 
 

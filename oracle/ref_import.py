@@ -201,3 +201,62 @@ def ref_intramodularConnectivity(adj: np.ndarray, colors, **kw):
     adj = np.array(adj, dtype=np.float64, copy=True)
     with _quiet(), np.errstate(all="ignore"):
         return W.WGCNA.intramodularConnectivity(adj, np.asarray(colors), **kw)
+
+
+# --------------------------------------------------------------------------------------------
+# end-to-end check: the reference's own clustering on top of a TOM (findModules, wgcna.py:323-334)
+# --------------------------------------------------------------------------------------------
+_CUTREE = None
+
+
+def _reference_cutreeHybrid():
+    """``WGCNA.cutreeHybrid`` with the two dependency-drift shims of SURVEY 8c: pandas >= 3
+    copy-on-write turns the chained assignment ``OrdNumLabs.Value[i] = ...`` (wgcna.py:1855, :1859)
+    into a no-op, and scipy >= 1.15 ``rankdata`` returns floats that the reference uses as indices
+    (wgcna.py:1452-1453).  The function source is otherwise executed unmodified."""
+    global _CUTREE
+    if _CUTREE is not None:
+        return _CUTREE
+    import inspect
+    import textwrap
+
+    from scipy import stats as _stats
+
+    W = load_reference()
+    src = textwrap.dedent(inspect.getsource(W.WGCNA.cutreeHybrid))
+    src = src.replace("@staticmethod\n", "")
+    assert src.count("OrdNumLabs.Value[i] = ") == 2
+    src = src.replace("OrdNumLabs.Value[i] = ", "OrdNumLabs.loc[i, 'Value'] = ")
+
+    def rankdata_int(*a, **k):
+        return _stats.rankdata(*a, **k).astype(np.int64)
+
+    class _StatsShim:
+        def __getattr__(self, name):
+            return rankdata_int if name == "rankdata" else getattr(_stats, name)
+
+    ns = dict(W.__dict__)
+    ns["rankdata"] = rankdata_int
+    ns["stats"] = _StatsShim()
+    exec(compile(src, "<reference cutreeHybrid, CoW-safe>", "exec"), ns)
+    _CUTREE = ns["cutreeHybrid"]
+    return _CUTREE
+
+
+def ref_modules_from_tom(tom: np.ndarray, minClusterSize=50, deepSplit=2, pamRespectsDendro=False):
+    """dissTOM -> linkage(average) -> cutreeHybrid exactly as findModules does (wgcna.py:323-334,
+    default kwargs of :265).  Returns (labels, linkage matrix)."""
+    from scipy.cluster.hierarchy import linkage
+    from scipy.spatial.distance import squareform
+
+    prev = pd.options.future.infer_string if hasattr(pd.options.future, "infer_string") else None
+    diss = pd.DataFrame(1 - np.asarray(tom, dtype=np.float64)).round(decimals=8)
+    a = squareform(diss.values, checks=False)
+    Z = linkage(a, method="average")
+    cut = _reference_cutreeHybrid()
+    with _quiet(), np.errstate(all="ignore"):
+        labels = cut(dendro=Z, distM=diss, minClusterSize=minClusterSize, deepSplit=deepSplit,
+                     pamRespectsDendro=pamRespectsDendro)
+    del prev
+    # cutreeHybrid returns the frame OrdNumLabs (wgcna.py:1848, :1864); "Value" holds the module labels
+    return np.asarray(labels["Value"], dtype=np.int64), Z

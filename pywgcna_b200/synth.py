@@ -17,12 +17,13 @@ CONFIGS = {
 
 
 def make_expression(m: int, n: int, F: int = 40, seed: int = 0, grey_frac: float = 0.3,
-                    neg_frac: float = 0.2, expression_like: bool = False, return_modules: bool = False):
+                    neg_frac: float = 0.2, expression_like: bool = False, return_modules: bool = False,
+                    loading=(0.4, 1.2)):
     rng = np.random.default_rng(seed)
     Z = rng.standard_normal((m, F))
     module = rng.integers(0, F, size=n)
     grey = rng.random(n) < grey_frac
-    lam = rng.uniform(0.4, 1.2, size=n)
+    lam = rng.uniform(loading[0], loading[1], size=n)
     lam[rng.random(n) < neg_frac] *= -1.0
     lam[grey] = 0.0
     X = rng.standard_normal((m, n))

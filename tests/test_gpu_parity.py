@@ -274,3 +274,30 @@ def test_multi_gpu_path_emulated_on_one_gpu(gpu, world, n):
     T = torch.cat([net.T[:net.nrows] for net in nets])
     assert not torch.isnan(T).any(), "a tile of the distributed schedule was never written"
     assert torch.equal(T, T_ref)
+
+
+def test_end_to_end_dendrogram_matches_reference(gpu, golden_dir):
+    """End-to-end check through the clustering findModules runs on top of the TOM (wgcna.py:323-328):
+    GPU pickSoftThreshold -> adjacency -> TOMsimilarity -> round(1 - TOM, 8) -> scipy linkage(average)
+    must give the dendrogram the unmodified reference produced (golden: same merges, same sizes, heights
+    to 1e-8), which is the input cutreeHybrid turns into module labels.  (The label comparison itself
+    needs the reference's cutreeHybrid, which does not travel to the GPU box: tools/e2e_labels.py.)"""
+    from scipy.cluster.hierarchy import linkage
+    from scipy.spatial.distance import squareform
+
+    g = load(golden_dir, "e2e_modules")
+    df = pd.DataFrame(g["X"])
+    p, sft = bw.pickSoftThreshold(df, networkType="signed hybrid", powerVector=list(g["powers"]))
+    assert int(p) == int(g["power"])
+    np.testing.assert_allclose(sft.to_numpy(dtype=float)[:, 4:], g["sft"][:, 4:], rtol=1e-10, atol=1e-10)
+    A = bw.adjacency(df, adjacencyType="signed hybrid", power=p)
+    for prec in PRECISIONS:
+        T = bw.TOMsimilarity(A.copy(), TOMType="signed", precision=prec)
+        assert maxabs(T.to_numpy()[:8], g["tom_sample"]) < TOL_TOM[prec]
+        diss = (1 - T).round(decimals=8)
+        Z = linkage(squareform(diss.values, checks=False), method="average")
+        Zref = g["linkage"]
+        assert np.array_equal(Z[:, [0, 1, 3]], Zref[:, [0, 1, 3]]), f"merge order differs ({prec})"
+        np.testing.assert_allclose(Z[:, 2], Zref[:, 2], rtol=0, atol=2e-8)
+        # the fused epilogue hand-off gives the same rounded dissimilarity
+        assert np.array_equal(bw.dissTOM(A.copy(), TOMType="signed", precision=prec), diss.values)

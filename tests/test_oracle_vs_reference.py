@@ -28,3 +28,16 @@ def test_pipeline_live(net):
     for tt in ["unsigned", "signed"]:
         T_ref = R.ref_TOMsimilarity(A_ref, TOMType=tt).to_numpy()
         np.testing.assert_allclose(O.TOMsimilarity(A_ref.copy(), TOMType=tt).to_numpy(), T_ref, rtol=0, atol=1e-13)
+
+
+def test_reference_clustering_harness_reproduces_golden_labels(golden_dir):
+    """The CoW-safe cutreeHybrid harness (oracle/ref_import.py) on the oracle's TOM gives the module
+    labels stored in the e2e fixture (which the same harness produced from the reference's TOM)."""
+    import os
+
+    g = np.load(os.path.join(golden_dir, "e2e_modules.npz"))
+    df = pd.DataFrame(g["X"])
+    A = O.adjacency(df, adjacencyType="signed hybrid", power=int(g["power"]))
+    T = O.TOMsimilarity(A, TOMType="signed").to_numpy()
+    labels, _ = R.ref_modules_from_tom(T, minClusterSize=30)
+    assert np.array_equal(labels, g["labels"]) and len(np.unique(labels)) == 6
