@@ -252,12 +252,10 @@ def run_ours(args):
         if not os.environ.get("B200W_BENCH_NOFLUSH"):
             flush.zero_()  # L2 flush between steps (256 MiB > 126 MB L2); the big operands exceed L2 anyway
         net_dev.standardize()
-        k = net_dev.sweep(powers)  # [P, n] on device
-        k_host = k.cpu().numpy()  # D2H of the connectivities (P * n * 8 bytes)
-        pv = np.sort(np.asarray(powers))
-        r2, _, _, mk, _, _ = W.fit_table(k_host, 10)  # the whole sft table of wgcna.py:924-932
-        ind = (r2 > 0.9) & (mk <= 100)
-        power = int(pv[ind].min()) if ind.any() else int(pv[np.argsort(r2)[-1]])
+        # sweep -> per-power histograms / medians / exact sums on the device -> the whole sft table of
+        # wgcna.py:924-932 (two 10-point regressions per power on the host) -> power selection :945-953
+        power, _table = net_dev.sft(powers, nBreaks=10, RsquaredCut=0.9, MeanCut=100)
+        power = int(power)
         net_dev.adjacency(power)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         # events around the contraction only: prepare + exchange happen inside tom() before compute,

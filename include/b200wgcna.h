@@ -75,6 +75,19 @@ int b200w_device_count(void);
 int b200w_connectivity_sweep(const double* X, int64_t m, int64_t n, const double* steps, int P,
                              int net_type, double* k_out, uint8_t* bad_out, int device);
 
+/* The sweep plus, still on the device, everything pickSoftThreshold derives from k[:, power] except
+ * the two 10-point regressions (wgcna.py:924-932, :1017-1034): per power a row of
+ *   stats[0] min, [1] max, [2] median (statistics.median), [3] float64 sum (informational),
+ *   [4 .. 4+nb) bin counts and [4+nb .. 4+2nb) bin sums of pd.cut(k, nb)  (right-closed bins, first edge
+ *   lowered by 0.1 % of the range, numpy linspace arithmetic),
+ * and buckets[p][e][2] = exact int64 sums of the low / high 27-bit halves of the 53-bit mantissas of all
+ * k with frexp exponent e - 1100 (b200w_sft_exp_buckets() entries per power), from which the host forms
+ * the exactly rounded statistics.mean (wgcna.py:930).  nbreaks <= 16.  k is not copied to the host. */
+int b200w_sft_exp_buckets(void);
+int b200w_soft_threshold_stats(const double* X, int64_t m, int64_t n, const double* steps, int P,
+                               int net_type, int nbreaks, double* stats_out, int64_t* buckets_out,
+                               int device);
+
 /* WGCNA.adjacency, wgcna.py:1097-1111 (corrcoef, transform, ** power).
  *   A_out    nrows x n row block of the n x n adjacency */
 int b200w_adjacency(const double* X, int64_t m, int64_t n, int net_type, double power,
@@ -133,6 +146,10 @@ int b200w_dev_standardize(const double* dX, int64_t m, int64_t n, double* dZ, ui
 int b200w_dev_sweep(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t n,
                     const double* h_steps, int P, int net_type, int64_t col0, int64_t ncols,
                     double* d_k /* P x ncols */, int device, void* stream);
+/* statistics of k[P, ldk >= n] as described at b200w_soft_threshold_stats; d_stats P x (4 + 2 nb),
+ * d_buckets P x b200w_sft_exp_buckets() x 2 */
+int b200w_dev_sft_stats(const double* d_k, int P, int64_t n, int64_t ldk, int nbreaks, double* d_stats,
+                        int64_t* d_buckets, int device, void* stream);
 int b200w_dev_adjacency(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t n, int net_type,
                         double power, int64_t row0, int64_t nrows, double* dA, int device,
                         void* stream);

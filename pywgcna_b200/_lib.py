@@ -42,6 +42,9 @@ SIGNATURES = {
     "b200w_last_error": (C.c_char_p, []),
     "b200w_device_count": (_int, []),
     "b200w_connectivity_sweep": (_int, [_dp, _i64, _i64, _dp, _int, _int, _dp, _dp, _int]),
+    "b200w_sft_exp_buckets": (_int, []),
+    "b200w_soft_threshold_stats": (_int, [_dp, _i64, _i64, _dp, _int, _int, _int, _dp, _dp, _int]),
+    "b200w_dev_sft_stats": (_int, [_dp, _int, _i64, _i64, _int, _dp, _dp, _int, _dp]),
     "b200w_adjacency": (_int, [_dp, _i64, _i64, _int, _dbl, _i64, _i64, _dp, _int]),
     "b200w_check_adjacency": (_int, [_dp, _i64, _dp, _int]),
     "b200w_tom": (_int, [_dp, _i64, _int, _int, _int, _int, _i64, _i64, _dp, _int, _dp, _int]),

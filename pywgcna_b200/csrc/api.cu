@@ -265,6 +265,40 @@ extern "C" int b200w_connectivity_sweep(const double* X, int64_t m, int64_t n, c
   return 0;
 }
 
+extern "C" int b200w_soft_threshold_stats(const double* X, int64_t m, int64_t n, const double* steps,
+                                          int P, int net_type, int nbreaks, double* stats_out,
+                                          int64_t* buckets_out, int device) {
+  if (!X || !steps || !stats_out || !buckets_out || m < 1 || n < 1 || P < 1 || nbreaks < 1 || nbreaks > 16)
+    return fail(B200W_E_INVALID, "soft_threshold_stats: bad args");
+  if (int e = ensure_device(device)) return e;
+  Stream st;
+  B200W_CUDA(st.create());
+  DevBuf dX, dZ, dBad, dK, dS, dB;
+  const int64_t ldk = b200w_padded_k(m);
+  const size_t sbytes = (size_t)P * (4 + 2 * nbreaks) * 8;
+  const size_t bbytes = (size_t)P * b200w_sft_exp_buckets() * 2 * 8;
+  B200W_CUDA(dX.alloc((size_t)m * n * 8));
+  B200W_CUDA(dZ.alloc((size_t)n * ldk * 8));
+  B200W_CUDA(dBad.alloc((size_t)n));
+  B200W_CUDA(dK.alloc((size_t)P * n * 8));
+  B200W_CUDA(dS.alloc(sbytes));
+  B200W_CUDA(dB.alloc(bbytes));
+  B200W_CUDA(cudaMemcpyAsync(dX.p, X, (size_t)m * n * 8, cudaMemcpyHostToDevice, st.s));
+  if (int e = b200w_dev_standardize(dX.as<double>(), m, n, dZ.as<double>(), dBad.as<uint8_t>(),
+                                    device, st.s))
+    return e;
+  if (int e = b200w_dev_sweep(dZ.as<double>(), dBad.as<uint8_t>(), m, n, steps, P, net_type, 0, n,
+                              dK.as<double>(), device, st.s))
+    return e;
+  if (int e = b200w_dev_sft_stats(dK.as<double>(), P, n, n, nbreaks, dS.as<double>(), dB.as<int64_t>(),
+                                  device, st.s))
+    return e;
+  B200W_CUDA(cudaMemcpyAsync(stats_out, dS.p, sbytes, cudaMemcpyDeviceToHost, st.s));
+  B200W_CUDA(cudaMemcpyAsync(buckets_out, dB.p, bbytes, cudaMemcpyDeviceToHost, st.s));
+  B200W_CUDA(cudaStreamSynchronize(st.s));
+  return 0;
+}
+
 extern "C" int b200w_adjacency(const double* X, int64_t m, int64_t n, int net_type, double power,
                                int64_t row0, int64_t nrows, double* A_out, int device) {
   if (!X || !A_out || m < 1 || n < 1 || row0 < 0 || nrows < 1 || row0 + nrows > n)

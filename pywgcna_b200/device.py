@@ -131,6 +131,34 @@ class DeviceNetwork:
         self._all_gather_rows(kT)
         return kT[:self.n].T.contiguous()
 
+    def sft(self, powers, nBreaks: int = 10, RsquaredCut: float = 0.9, MeanCut: float = 100):
+        """Device-resident ``pickSoftThreshold`` (wgcna.py:873-953): sweep, then histograms, medians and
+        exact mantissa sums on the device; 2 x P ten-point regressions on the host.  Returns
+        (selected power, dict of the six table columns)."""
+        from . import wgcna as W
+
+        pv = np.sort(np.asarray(powers))
+        k = self.sweep(pv)  # [P, n]
+        P = len(pv)
+        if not hasattr(self, "_sft_bufs") or self._sft_bufs[0].shape[0] != P or self._sft_bufs[3] != nBreaks:
+            E = self.lib.b200w_sft_exp_buckets()
+            self._sft_bufs = (torch.empty((P, 4 + 2 * nBreaks), dtype=torch.float64, device=self.dev),
+                              torch.empty((P, E, 2), dtype=torch.int64, device=self.dev),
+                              (torch.empty((P, 4 + 2 * nBreaks), dtype=torch.float64).pin_memory(),
+                               torch.empty((P, E, 2), dtype=torch.int64).pin_memory()), nBreaks)
+        d_stats, d_buck, (h_stats, h_buck), _ = self._sft_bufs
+        L.check(self.lib.b200w_dev_sft_stats(k.data_ptr(), P, self.n, k.stride(0), nBreaks, d_stats.data_ptr(),
+                                             d_buck.data_ptr(), self.device, self._stream()))
+        h_stats.copy_(d_stats, non_blocking=True)
+        h_buck.copy_(d_buck, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        r2, slope, r2adj, mean, med, mx = W.fit_table_from_stats(h_stats.numpy(), h_buck.numpy(), self.n, nBreaks)
+        with np.errstate(invalid="ignore"):
+            ind = (r2 > RsquaredCut) & (mean <= MeanCut)  # wgcna.py:945
+        power = pv[ind].min() if ind.any() else pv[np.argsort(r2)[-1]]
+        return power, {"SFT.R.sq": r2, "slope": slope, "truncated R.sq": r2adj, "mean(k)": mean,
+                       "median(k)": med, "max(k)": mx}
+
     def adjacency(self, power: float) -> torch.Tensor:
         """This rank's row block of the adjacency (wgcna.py:1097-1111), kept in HBM."""
         if not self._standardized:

@@ -229,6 +229,48 @@ def fit_table(K: np.ndarray, nBreaks: int = 10):
     return r1, b1[:, 1], r2adj, mean, med, mx
 
 
+def fit_table_from_stats(stats: np.ndarray, buckets: np.ndarray, n: int, nBreaks: int = 10):
+    """``fit_table`` from the per-power statistics the device computed (``b200w_dev_sft_stats``):
+    stats [P, 4 + 2 nb] (min, max, median, sum, counts, bin sums), buckets [P, E, 2] exact mantissa
+    sums.  Only the two batched 10-point regressions and the assembly of the exact mean run here."""
+    stats = np.asarray(stats, dtype=np.float64)
+    P = stats.shape[0]
+    mn, mx, med = stats[:, 0], stats[:, 1], stats[:, 2]
+    cnt = stats[:, 4:4 + nBreaks]
+    tot = stats[:, 4 + nBreaks:4 + 2 * nBreaks]
+    mean = np.empty(P)
+    bk = np.asarray(buckets).reshape(P, -1, 2)
+    for p in range(P):
+        nzb = np.nonzero((bk[p, :, 0] != 0) | (bk[p, :, 1] != 0))[0]
+        if nzb.size == 0:
+            mean[p] = 0.0 if np.isfinite(stats[p, 3]) else stats[p, 3] / n
+            continue
+        e0 = int(nzb[0])
+        total = 0
+        for e in nzb.tolist():
+            total += ((int(bk[p, e, 1]) << 27) + int(bk[p, e, 0])) << (e - e0)
+        ex = e0 - 1100 - 53  # value = total * 2^ex
+        frac = Fraction(total * (1 << ex), n) if ex >= 0 else Fraction(total, n * (1 << -ex))
+        mean[p] = float(frac)
+    with np.errstate(all="ignore"):
+        dk = tot / cnt  # NaN where a bin is empty (:1019)
+        p_dk = cnt / n  # (:1022)
+        step = (mx - mn) / nBreaks  # np.linspace(min k, max k, nBreaks + 1) (:1025)
+        grid = np.arange(nBreaks + 1)[None, :] * step[:, None] + mn[:, None]
+        grid[:, -1] = mx
+        mids = 0.5 * (grid[:, 1:] + grid[:, :-1])  # (:1027)
+        empty = np.isnan(dk)
+        dk = np.where(empty, mids, dk)  # (:1029-1030)
+        dk = np.where(dk == 0, mids, dk)  # (:1031-1032)
+        log_dk = np.log10(dk)  # (:1035)
+        log_p = np.log10(p_dk + 1e-09)  # (:1036)
+        trunc = np.power(10, log_dk)  # (:1037)
+        ones = np.ones_like(log_dk)
+        b1, r1, _ = _ols_batch(log_p, np.stack([ones, log_dk], axis=2))  # (:1039)
+        _, _, r2adj = _ols_batch(log_p, np.stack([ones, log_dk, trunc], axis=2))  # (:1040)
+    return r1, b1[:, 1], r2adj, mean, med.copy(), mx.copy()
+
+
 def calBlockSize(matrixSize, rectangularBlocks=True, maxMemoryAllocation=None, overheadFactor=3):
     """``WGCNA.calBlockSize`` (wgcna.py:988-1004).  Only reported for log parity: the CUDA sweep
     tiles the n x n problem on chip and needs no host block size."""
@@ -296,10 +338,23 @@ def pickSoftThreshold(data, dataIsExpr=True, weights=None, RsquaredCut=0.9, Mean
     datout = pd.DataFrame(np.full((len(powerVector), len(colname1)), 666), columns=colname1, dtype=object)
     datout["Power"] = powerVector
 
-    datk = connectivity(data, powerVector, networkType, device=device)
-
-    # :924-932, all powers at once (datk is the transpose view of the kernel's [P, n] output)
-    stats = fit_table(np.ascontiguousarray(datk.T), nBreaks)
+    if 1 <= nBreaks <= 16:
+        # sweep, histograms, medians and exact mantissa sums on the device (k never leaves HBM); only
+        # the two 10-point regressions per power run on the host                       (:873-932)
+        X = L.as_f64_matrix(data)
+        m_, n_ = X.shape
+        pv = np.asarray(powerVector, dtype=np.float64)
+        steps = np.ascontiguousarray(np.diff(np.concatenate(([0.0], pv))))  # :901-903
+        lib = L.load()
+        dstats = np.empty((len(pv), 4 + 2 * nBreaks), dtype=np.float64)
+        dbuck = np.empty((len(pv), lib.b200w_sft_exp_buckets(), 2), dtype=np.int64)
+        L.check(lib.b200w_soft_threshold_stats(L.hptr(X), m_, n_, L.hptr(steps), len(pv),
+                                               networkTypes.index(networkType), nBreaks, L.hptr(dstats),
+                                               L.hptr(dbuck), _device(device)))
+        stats = fit_table_from_stats(dstats, dbuck, n_, nBreaks)
+    else:
+        datk = connectivity(data, powerVector, networkType, device=device)
+        stats = fit_table(np.ascontiguousarray(datk.T), nBreaks)  # :924-932, all powers at once
     for name, col in zip(colname1[1:], stats):
         datout[name] = pd.Series(list(col), dtype=object)
     _say(datout)

@@ -301,3 +301,32 @@ def test_end_to_end_dendrogram_matches_reference(gpu, golden_dir):
         np.testing.assert_allclose(Z[:, 2], Zref[:, 2], rtol=0, atol=2e-8)
         # the fused epilogue hand-off gives the same rounded dissimilarity
         assert np.array_equal(bw.dissTOM(A.copy(), TOMType="signed", precision=prec), diss.values)
+
+
+@pytest.mark.parametrize("n", [1001, 4000])
+def test_device_sft_statistics(gpu, n):
+    """Device histograms / medians / exact sums (b200w_dev_sft_stats) against the host fit on the same k:
+    mean, median and max bit-identical to statistics.mean / statistics.median / max, regressions to 1e-9."""
+    import statistics
+
+    import torch
+
+    from pywgcna_b200 import wgcna as W
+    from pywgcna_b200.device import DeviceNetwork
+
+    X = make_expression(70, n, F=6, seed=n)
+    X[:, 3] = 1.5  # a NaN gene: k = 0 for it
+    powers = list(range(1, 21))
+    net = DeviceNetwork(X, device=0, networkType="signed hybrid")
+    power, tab = net.sft(powers)
+    k = net.sweep(powers).cpu().numpy()
+    r2, slope, r2adj, mean, med, mx = W.fit_table(k, 10)
+    assert np.array_equal(tab["mean(k)"], mean) and np.array_equal(tab["median(k)"], med)
+    assert np.array_equal(tab["max(k)"], mx)
+    for i in (0, 7, 19):
+        assert tab["mean(k)"][i] == statistics.mean(k[i]) and tab["median(k)"][i] == statistics.median(k[i])
+    np.testing.assert_allclose(tab["SFT.R.sq"], r2, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(tab["slope"], slope, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(tab["truncated R.sq"], r2adj, rtol=1e-9, atol=1e-11)
+    p_ref, _ = O.pickSoftThreshold(pd.DataFrame(X), networkType="signed hybrid", powerVector=powers, faithful=False)
+    assert int(power) == int(p_ref)
