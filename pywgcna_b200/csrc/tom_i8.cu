@@ -246,12 +246,14 @@ struct I8Cfg {
 template <int kStages>
 struct __align__(8) I8Barriers {
   uint64_t full[kStages], empty[kStages], tmem_full[2], tmem_empty[2];
+  uint64_t fin_full[2], fin_empty[2];  // epilogue warps -> finalizer warps hand-off of a finished tile's sums
   uint32_t tmem_base;
 };
 
 template <int kCtas>
 __host__ __device__ constexpr size_t i8_smem_bytes() {
-  return (size_t)I8Cfg<kCtas>::kStages * I8Cfg<kCtas>::kStageBytes + sizeof(I8Barriers<I8Cfg<kCtas>::kStages>) + 1024;
+  return (size_t)I8Cfg<kCtas>::kStages * I8Cfg<kCtas>::kStageBytes + sizeof(I8Barriers<I8Cfg<kCtas>::kStages>) +
+         1024;
 }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -317,6 +319,8 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bars->tmem_full[a], 1);
       mbar_init(&bars->tmem_empty[a], 4 * kCtas);  // one arrive per epilogue warp of every CTA
+      mbar_init(&bars->fin_full[a], 4);            // the 4 epilogue warps of this CTA
+      mbar_init(&bars->fin_empty[a], 2);           // the 2 finalizer warps of this CTA
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -460,63 +464,38 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ======================================= epilogue =======================================
+    // ================ epilogue: TMEM accumulator -> float64 running sum in scratch ===============
+    // Every pass is drained at once (coalesced scratch, lanes = rows) and the accumulator handed back
+    // to the MMA warp.  The TOM formula and the n x n stores are NOT done here: measured at C2, doing
+    // them before / after the release exposed 10 / 7 ms of 43, because these four warps were still busy
+    // when the next accumulator filled.  The finished sums go to the two finalizer warps through a
+    // double-buffered scratch tile.
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
-    double* scratch = p.scratch + (int64_t)blockIdx.x * (kTM * kTN);
     int acc = 0;
     uint32_t acc_phase = 0;
+    int64_t done = 0;
     for (int64_t it = 0; it < iters; ++it) {
       const int64_t tile = unit + it * n_units;
       if (tile >= n_tiles) break;
-      const int2 t2 = p.tile_list[tile];
-      const int64_t tm = t2.x, tn = t2.y;
-      const int64_t gi = p.tile_row_base + tm * Cfg::kTileRows + rank * kTM + row, j0 = tn * kTN;
-      // symmetric schedule: TOM_ji = TOM_ij, stored from the same registers; for a fixed column the 32
-      // lanes of a warp hold 32 consecutive rows, so the mirrored store is one coalesced 256-byte line
-      // (in a diagonal tile only the entries on and above the diagonal are stored, with their mirror);
-      // the mirrored row gj may belong to another GPU: the store then goes to that GPU's HBM
-      const bool mirror = p.symmetric != 0;
-      const bool diag_tile = p.tile_row_base + tm * Cfg::kTileRows == tn * kTN;
-      const bool row_ok = gi < p.row0 + p.nrows;
-      const double ki = row_ok ? p.k[gi] : 0.0;
-      const double si = row_ok ? p.scale[gi] * p.final_scale : 0.0;
-      const double* arow = p.A_rows + (row_ok ? (gi - p.row0) : 0) * p.n;
-      double* orow = p.out + (row_ok ? (gi - p.row0) : 0) * p.n;
+      const int buf = (int)(done & 1);
+      double* scratch = p.scratch + ((int64_t)blockIdx.x * 2 + buf) * (kTM * kTN);
+      mbar_wait(&bars->fin_empty[buf], (uint32_t)((done >> 1) & 1) ^ 1);  // finalizers are done with this buffer
       for (int ps = 0; ps < p.npass; ++ps) {
         mbar_wait(&bars->tmem_full[acc], acc_phase);
         tc_fence_after();
         const double w = p.pass_w[ps];
-        const bool first = ps == 0, last = ps + 1 == p.npass;
+        const bool first = ps == 0;
 #pragma unroll 1
         for (int c = 0; c < kTN / 32; ++c) {
           uint32_t r[32];
           tc_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kTN + c * 32), r);
           double* sc = scratch + (int64_t)c * 32 * kTM + row;  // [c][col][row]: lanes = consecutive rows
-          if (!last) {
 #pragma unroll
-            for (int col = 0; col < 32; ++col) {
-              double v = (double)(int)r[col] * w;
-              if (!first) v += sc[col * kTM];
-              sc[col * kTM] = v;
-            }
-          } else {
-#pragma unroll
-            for (int col = 0; col < 32; ++col) {
-              double v = (double)(int)r[col] * w;
-              if (!first) v += sc[col * kTM];
-              const int64_t gj = j0 + c * 32 + col;
-              if (row_ok && gj < p.n && !(mirror && diag_tile && gj < gi)) {
-                const double L = v * (si * p.scale[gj]);
-                const double a = tom_clean(arow[gj], gi, gj);
-                const double t = tom_value(L, a, ki, p.k[gj], gi == gj, p.tom_type, p.tom_denom, p.out_mode);
-                orow[gj] = t;
-                if (mirror && !(diag_tile && gj <= gi)) {
-                  const int64_t owner = gj / p.per_rows;
-                  p.peer_out[owner][(gj - owner * p.per_rows) * p.n + gi] = t;
-                }
-              }
-            }
+          for (int col = 0; col < 32; ++col) {
+            double v = (double)(int)r[col] * w;
+            if (!first) v += sc[col * kTM];
+            sc[col * kTM] = v;
           }
         }
         tc_fence_before();
@@ -527,6 +506,81 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->fin_full[buf]);  // release: the sums of this tile are in scratch
+      ++done;
+    }
+  } else {
+    // ====== finalizers (warps 2 and 3): TOM formula + stores of a finished tile, off the MMA path ======
+    // symmetric schedule: TOM_ji = TOM_ij, stored from the same registers; for a fixed column the 32
+    // lanes of a warp hold 32 consecutive rows, so the mirrored store is one coalesced 256-byte line
+    // (in a diagonal tile only the entries on and above the diagonal are stored, with their mirror);
+    // the mirrored row gj may belong to another GPU: the store then goes to that GPU's HBM
+    const int f = warp - 2;
+    const bool mirror = p.symmetric != 0;
+    int64_t done = 0;
+    for (int64_t it = 0; it < iters; ++it) {
+      const int64_t tile = unit + it * n_units;
+      if (tile >= n_tiles) break;
+      const int2 t2 = p.tile_list[tile];
+      const int64_t tm = t2.x, tn = t2.y;
+      const int64_t j0 = tn * kTN;
+      const bool diag_tile = p.tile_row_base + tm * Cfg::kTileRows == tn * kTN;
+      const int buf = (int)(done & 1);
+      const double* scratch = p.scratch + ((int64_t)blockIdx.x * 2 + buf) * (kTM * kTN);
+      mbar_wait(&bars->fin_full[buf], (uint32_t)((done >> 1) & 1));
+      // Latency, not bandwidth, is what this phase fights (one warp = one 32-row slab, little else to
+      // switch to): all loads of a half chunk are issued up front and unconditionally (clamped addresses),
+      // per-column scale / k come from one coalesced load per lane + shuffles, and only the stores are
+      // predicated.  (With the loads inside the per-element branch this loop ran ~3700 cycles per element
+      // and throttled the whole kernel through the scratch hand-off.)
+#pragma unroll 1
+      for (int slab = 2 * f; slab < 2 * f + 2; ++slab) {
+        const int row = slab * 32 + lane;
+        const int64_t gi = p.tile_row_base + tm * Cfg::kTileRows + rank * kTM + row;
+        const bool row_ok = gi < p.row0 + p.nrows;
+        const int64_t gic = row_ok ? gi : p.row0 + p.nrows - 1;  // clamped row for the loads
+        const double ki = p.k[gic];
+        const double si = p.scale[gic] * p.final_scale;
+        const double* arow = p.A_rows + (gic - p.row0) * p.n;
+        double* orow = p.out + (gic - p.row0) * p.n;
+#pragma unroll 1
+        for (int c = 0; c < kTN / 32; ++c) {
+          const int64_t gjl = j0 + c * 32 + lane;
+          const int64_t gjc = gjl < p.n ? gjl : p.n - 1;
+          const double sj_l = p.scale[gjc], kj_l = p.k[gjc];  // column values: one per lane, shuffled below
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const double* sc = scratch + ((int64_t)c * 32 + h * 16) * kTM + row;
+            const int64_t gj0 = j0 + c * 32 + h * 16;
+            double scv[16], av[16];
+#pragma unroll
+            for (int col = 0; col < 16; ++col) {
+              scv[col] = sc[col * kTM];
+              const int64_t gj = gj0 + col;
+              av[col] = arow[gj < p.n ? gj : p.n - 1];
+            }
+#pragma unroll
+            for (int col = 0; col < 16; ++col) {
+              const int64_t gj = gj0 + col;
+              const double sj = __shfl_sync(0xffffffffu, sj_l, h * 16 + col);
+              const double kj = __shfl_sync(0xffffffffu, kj_l, h * 16 + col);
+              const double L = scv[col] * (si * sj);
+              const double a = tom_clean(av[col], gi, gj);
+              const double t = tom_value(L, a, ki, kj, gi == gj, p.tom_type, p.tom_denom, p.out_mode);
+              const bool ok = row_ok && gj < p.n;
+              if (ok && !(mirror && diag_tile && gj < gi)) orow[gj] = t;
+              if (ok && mirror && !(diag_tile && gj <= gi)) {
+                const int64_t owner = gj / p.per_rows;
+                p.peer_out[owner][(gj - owner * p.per_rows) * p.n + gi] = t;
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->fin_empty[buf]);
+      ++done;
     }
   }
   tc_fence_before();
@@ -732,7 +786,7 @@ int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t o
   const int64_t units = n_tiles < sms / ctas ? n_tiles : sms / ctas;
   const int grid = (int)(units * ctas);
   Scratch scratch;
-  B200W_CUDA(scratch.alloc((size_t)grid * kTM * kTN * sizeof(double), st));
+  B200W_CUDA(scratch.alloc((size_t)grid * 2 * kTM * kTN * sizeof(double), st));  // two tiles per CTA
   prm.scratch = scratch.as<double>();
   prm.sync_mode = 3;
   if (const char* e = getenv("B200W_I8_SYNC")) prm.sync_mode = atoi(e);
