@@ -336,9 +336,16 @@ def run_ours(args):
     peak_src = "measured bf16 burst (MEASURED_PEAKS.json)" if "bf16_tflops" in peaks else "fallback 1590"
     if prec_name == "i8":
         mmas = int(os.environ.get("B200W_I8_PAIRS", "15"))
-        peak = 2.0 * bf16 / mmas
-        peak_note = (f"kind::i8 peak taken as 2 x {peak_src} = {2 * bf16:.0f} TOP/s (not separately measured) "
-                     f"/ {mmas} slice-pair MMAs per logical product")
+        try:
+            i8 = json.load(open(os.path.join(ROOT, "profiles", "r01_int8_peak.json")))
+            i8_tops = float(i8["int8_tops_burst"])
+            i8_src = ("int8 GEMM peak measured with MEASURED_PEAKS.json's method (cuBLASLt via torch._int_mm 8192^3, "
+                      f"burst; sustained {i8['int8_tops_sustained']:.0f}; tcgen05 issue-rate ceiling "
+                      f"{i8['tcgen05_issue_rate_tops']:.0f}) -- profiles/r01_int8_peak.json")
+        except Exception:
+            i8_tops, i8_src = 2.0 * bf16, f"2 x {peak_src} (int8 not separately measured)"
+        peak = i8_tops / mmas
+        peak_note = f"{i8_tops:.0f} TOP/s [{i8_src}] / {mmas} digit-pair s8 MMAs per logical float64-grade product"
     else:
         peak = 37.0
         peak_note = "FP64 DMMA nominal 37 TFLOP/s (HGX B200 spec; MEASURED_PEAKS.json has no f64 figure)"
