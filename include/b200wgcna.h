@@ -50,6 +50,10 @@ extern "C" {
 #define B200W_OUT_TOM 0      /* TOM, diagonal 1                 (wgcna.py:1153-1156) */
 #define B200W_OUT_DISS 1     /* 1 - TOM                         (wgcna.py:323)       */
 #define B200W_OUT_DISS_R8 2  /* rint((1 - TOM) * 1e8) / 1e8     (wgcna.py:323-324)   */
+/* condensed outputs (whole matrix only): the n (n - 1) / 2 entries above the diagonal, row by row --
+ * exactly what scipy's squareform(dissTOM, checks=False) hands to linkage (wgcna.py:326-328) */
+#define B200W_OUT_DISS_COND 3     /* 1 - TOM, condensed                */
+#define B200W_OUT_DISS_R8_COND 4  /* round(1 - TOM, 8), condensed      */
 /* arithmetic of the A.A contraction */
 #define B200W_PREC_AUTO 0    /* = B200W_PREC_I8 */
 #define B200W_PREC_F64 1     /* FP64 tensor-core DMMA (mma.sync f64)                    */

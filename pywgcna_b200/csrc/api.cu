@@ -351,7 +351,11 @@ static int tom_from_device_adjacency(const double* dA, int64_t n, int tom_type, 
   B200W_CUDA(dScale.alloc((size_t)round_up(n, 128) * 8));
   B200W_CUDA(dK.alloc((size_t)round_up(n, 128) * 8));
   B200W_CUDA(cudaMemsetAsync(dOp.p, 0, (size_t)b200w_tom_operand_bytes(n, precision), s));
-  B200W_CUDA(dOut.alloc((size_t)nrows * n * 8));
+  const bool condensed = out_mode == B200W_OUT_DISS_COND || out_mode == B200W_OUT_DISS_R8_COND;
+  if (condensed && (row0 != 0 || nrows != n))
+    return fail(B200W_E_INVALID, "tom: condensed output needs the whole matrix");
+  const size_t out_bytes = condensed ? (size_t)n * (n - 1) / 2 * 8 : (size_t)nrows * n * 8;
+  B200W_CUDA(dOut.alloc(out_bytes));
   const int64_t op_rows = round_up(n, 128);
   if (int e = b200w_dev_tom_prepare(dA, n, 0, n, precision, dOp.p, op_rows, dScale.as<double>(),
                                     dK.as<double>(), device, s))
@@ -360,7 +364,7 @@ static int tom_from_device_adjacency(const double* dA, int64_t n, int tom_type, 
                                     dK.as<double>(), n, row0, nrows, tom_type, tom_denom, out_mode, precision,
                                     dOut.as<double>(), device, s))
     return e;
-  B200W_CUDA(cudaMemcpyAsync(out_host, dOut.p, (size_t)nrows * n * 8, cudaMemcpyDeviceToHost, s));
+  B200W_CUDA(cudaMemcpyAsync(out_host, dOut.p, out_bytes, cudaMemcpyDeviceToHost, s));
   B200W_CUDA(cudaStreamSynchronize(s));
   return 0;
 }
@@ -377,7 +381,8 @@ extern "C" int b200w_tom(const double* A, int64_t n, int tom_type, int tom_denom
   DevBuf dA;
   HostPin pin_in, pin_out;
   pin_in.pin(A, (size_t)n * n * 8);
-  pin_out.pin(out, (size_t)nrows * n * 8);
+  pin_out.pin(out, (out_mode == B200W_OUT_DISS_COND || out_mode == B200W_OUT_DISS_R8_COND)
+                       ? (size_t)n * (n - 1) / 2 * 8 : (size_t)nrows * n * 8);
   B200W_CUDA(dA.alloc((size_t)n * n * 8));
   B200W_CUDA(cudaMemcpyAsync(dA.p, A, (size_t)n * n * 8, cudaMemcpyHostToDevice, st.s));
   if (check) {

@@ -138,8 +138,10 @@ tom_f64_kernel(const double* __restrict__ A_rows, const double* __restrict__ Ac,
           const int64_t gj = j0 + wn * 32 + ni * 8 + 2 * tig + cb;
           if (gj >= n) continue;
           const double a = tom_clean(arow[gj], gi, gj);
-          orow[gj] = tom_value(acc.v[mi][ni][ch * 2 + cb], a, ki, k[gj], gi == gj, tom_type,
-                               tom_denom, out_mode);
+          const double t = tom_value(acc.v[mi][ni][ch * 2 + cb], a, ki, k[gj], gi == gj, tom_type,
+                                     tom_denom, out_mode);
+          if (!out_is_condensed(out_mode)) orow[gj] = t;
+          else if (gj > gi) out[condensed_index(n, gi, gj)] = t;
         }
       }
     }
@@ -249,8 +251,10 @@ extern "C" int b200w_dev_tom_compute(const double* dA_rows, const void* d_operan
     return fail(B200W_E_INVALID, "tom_compute: bad args");
   if (op_rows < round_up(n, 128) || op_rows % 128)
     return fail(B200W_E_INVALID, "tom_compute: op_rows must be a multiple of 128 >= n");
-  if (tom_type < 0 || tom_type > 1 || tom_denom < 0 || tom_denom > 1 || out_mode < 0 || out_mode > 2)
+  if (tom_type < 0 || tom_type > 1 || tom_denom < 0 || tom_denom > 1 || out_mode < 0 || out_mode > 4)
     return fail(B200W_E_INVALID, "tom_compute: bad enum");
+  if (out_is_condensed(out_mode) && (row0 != 0 || nrows != n))
+    return fail(B200W_E_INVALID, "tom_compute: condensed output needs the whole matrix (row0 = 0, nrows = n)");
   precision = resolve_precision(precision);
   if (int e = ensure_device(device)) return e;
   cudaStream_t st = (cudaStream_t)stream;

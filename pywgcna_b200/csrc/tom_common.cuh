@@ -25,8 +25,17 @@ __device__ __forceinline__ double tom_value(double L, double a, double ki, doubl
   }
   if (out_mode == B200W_OUT_TOM) return t;
   t = 1.0 - t;
-  if (out_mode == B200W_OUT_DISS_R8) t = rint(t * 1e8) / 1e8;  // numpy around(decimals=8)
+  if (out_mode == B200W_OUT_DISS_R8 || out_mode == B200W_OUT_DISS_R8_COND)
+    t = rint(t * 1e8) / 1e8;  // numpy around(decimals=8)
   return t;
+}
+
+__host__ __device__ __forceinline__ bool out_is_condensed(int out_mode) {
+  return out_mode == B200W_OUT_DISS_COND || out_mode == B200W_OUT_DISS_R8_COND;
+}
+// index of (i, j), i < j, in scipy's condensed distance vector
+__device__ __forceinline__ int64_t condensed_index(int64_t n, int64_t i, int64_t j) {
+  return n * i - i * (i + 1) / 2 + (j - i - 1);
 }
 
 __device__ __forceinline__ double block_sum_256(double v) {

@@ -569,6 +569,10 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
               const double a = tom_clean(av[col], gi, gj);
               const double t = tom_value(L, a, ki, kj, gi == gj, p.tom_type, p.tom_denom, p.out_mode);
               const bool ok = row_ok && gj < p.n;
+              if (out_is_condensed(p.out_mode)) {  // entries above the diagonal only, squareform order
+                if (ok && gj > gi) p.out[condensed_index(p.n, gi, gj)] = t;
+                continue;
+              }
               if (ok && !(mirror && diag_tile && gj < gi)) orow[gj] = t;
               if (ok && mirror && !(diag_tile && gj <= gi)) {
                 const int64_t owner = gj / p.per_rows;

@@ -443,7 +443,8 @@ def _tom(adjMat, TOMTypeC, TOMDenomC, check, out_mode=L.OUT_TOM, device=None, ro
     A = np.ascontiguousarray(adjMat, dtype=np.float64)
     n = A.shape[0]
     row0, nrows = (0, n) if rows is None else (int(rows[0]), int(rows[1]))
-    out = L.result_empty((nrows, n))
+    condensed = out_mode in (L.OUT_DISS_COND, L.OUT_DISS_R8_COND)
+    out = L.result_empty((n * (n - 1) // 2,) if condensed else (nrows, n))
     stats = np.full(4, np.nan)
     prec = _PREC[(precision or PRECISION).lower()]
     rc = L.load().b200w_tom(L.hptr(A), n, TOMTypeC, TOMDenomC, out_mode, prec, row0, nrows, L.hptr(out),
@@ -481,14 +482,19 @@ def TOMsimilarity(adjMat, TOMType="signed", TOMDenom="min", device=None, precisi
     return pd.DataFrame(tom, copy=False)
 
 
-def dissTOM(adjMat, TOMType="signed", TOMDenom="min", decimals=8, device=None, precision=None):
-    """Fused hand-off of findModules (wgcna.py:320-324): ``(1 - TOM).round(8)`` straight from the
-    TOM epilogue, as an ndarray."""
+def dissTOM(adjMat, TOMType="signed", TOMDenom="min", decimals=8, condensed=False, device=None, precision=None):
+    """Fused hand-off of findModules (wgcna.py:320-326): ``(1 - TOM).round(8)`` straight from the TOM
+    epilogue, as an ndarray; ``condensed=True`` returns the 1-D vector
+    ``squareform((1 - TOM).round(8), checks=False)`` that ``linkage`` consumes (wgcna.py:326-328) --
+    half the device-to-host bytes and no host pass over n^2."""
     TOMTypeC = TOMTypes.index(TOMType)
     TOMDenomC = TOMDenoms.index(TOMDenom)
     if decimals not in (None, 8):
         raise ValueError("decimals must be 8 (findModules) or None (no rounding)")
-    mode = L.OUT_DISS if decimals is None else L.OUT_DISS_R8
+    if condensed:
+        mode = L.OUT_DISS_COND if decimals is None else L.OUT_DISS_R8_COND
+    else:
+        mode = L.OUT_DISS if decimals is None else L.OUT_DISS_R8
     return _tom(adjMat, TOMTypeC, TOMDenomC, check=True, out_mode=mode, device=device, precision=precision)
 
 

@@ -165,6 +165,11 @@ def test_oracle_tom(gpu, prec, n):
     A = As
     D = bw.dissTOM(A.copy(), precision=prec)
     assert np.array_equal(D, (1 - T).round(decimals=8))
+    # condensed hand-off == scipy squareform of the rounded dissimilarity (wgcna.py:326)
+    from scipy.spatial.distance import squareform
+
+    Dc = bw.dissTOM(A.copy(), precision=prec, condensed=True)
+    assert Dc.shape == (n * (n - 1) // 2,) and np.array_equal(Dc, squareform(D, checks=False))
 
 
 def test_fused_network_matches_two_calls(gpu):
@@ -330,3 +335,20 @@ def test_device_sft_statistics(gpu, n):
     np.testing.assert_allclose(tab["truncated R.sq"], r2adj, rtol=1e-9, atol=1e-11)
     p_ref, _ = O.pickSoftThreshold(pd.DataFrame(X), networkType="signed hybrid", powerVector=powers, faithful=False)
     assert int(power) == int(p_ref)
+
+
+@pytest.mark.parametrize("n,m", [(3, 4), (5, 9), (17, 4), (127, 9), (129, 4), (255, 9), (257, 4)])
+def test_tiny_and_ragged_sizes(gpu, n, m):
+    """Sizes below / straddling every tile (128-row DMMA tiles, 256 x 256 tcgen05 tiles, 128-byte K blocks)."""
+    rng = np.random.default_rng(n * 31 + m)
+    df = pd.DataFrame(rng.standard_normal((m, n)))
+    p, sft = bw.pickSoftThreshold(df, networkType="unsigned", powerVector=[1, 2, 3, 5])
+    p0, sft0 = O.pickSoftThreshold(df, networkType="unsigned", powerVector=[1, 2, 3, 5], faithful=False)
+    assert int(p) == int(p0)
+    np.testing.assert_allclose(sft.to_numpy(float)[:, 4:], sft0.to_numpy(float)[:, 4:], rtol=1e-10, atol=1e-10)
+    A = bw.adjacency(df, power=2)
+    A0 = O.adjacency(df, power=2)
+    assert maxabs(A, A0) < TOL_F64
+    T0 = O.TOMsimilarity(A0.copy(), TOMType="unsigned").to_numpy()
+    for prec in PRECISIONS:
+        assert maxabs(bw.TOMsimilarity(A.copy(), TOMType="unsigned", precision=prec).to_numpy(), T0) < TOL_TOM[prec]
