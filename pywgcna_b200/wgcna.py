@@ -435,6 +435,30 @@ def checkAdjMat(adjMat, min=0, max=1, device=None):
         _raise_check(2, min, max)
 
 
+def checkSimilarity(adjMat, min=-1, max=1, device=None):
+    """``WGCNA.checkSimilarity`` (wgcna.py:958-985): the similarity-matrix flavour of ``checkAdjMat``
+    (only reached through ``pickSoftThreshold(dataIsExpr=False)``, a branch that cannot run in the
+    reference, wgcna.py:839); same three n^2 reductions on the GPU, the reference's messages."""
+    if hasattr(adjMat, "to_numpy"):
+        adjMat = adjMat.to_numpy()
+    dim = np.shape(adjMat)
+    if dim is None or len(dim) != 2:
+        sys.exit("adjacency is not two-dimensional")
+    if not np.issubdtype(np.asarray(adjMat).dtype, np.float64):
+        sys.exit("adjacency is not numeric")
+    if dim[0] != dim[1]:
+        sys.exit("adjacency is not square")
+    A = np.ascontiguousarray(adjMat, dtype=np.float64)
+    stats = np.empty(4, dtype=np.float64)
+    L.check(L.load().b200w_check_adjacency(L.hptr(A), A.shape[0], L.hptr(stats), _device(device)))
+    if stats[3] > 0:
+        return
+    if stats[0] > 1e-12:
+        sys.exit("adjacency is not symmetric")
+    if stats[1] < min or stats[2] > max:
+        sys.exit(f"some entries are not between {min} and {max}.")
+
+
 def _tom(adjMat, TOMTypeC, TOMDenomC, check, out_mode=L.OUT_TOM, device=None, rows=None, precision=None):
     if hasattr(adjMat, "to_numpy"):
         adjMat = adjMat.to_numpy()
@@ -586,8 +610,8 @@ def intramodularConnectivity(mat, colors, scaleByMax=False, index=None, device=N
 # ----------------------------------------------------------------------------------------------
 # drop-in installation
 # ----------------------------------------------------------------------------------------------
-_PATCHED = ("pickSoftThreshold", "scaleFreeFitIndex", "adjacency", "checkAdjMat", "TOMsimilarity",
-            "TomSimilarityFromAdj", "intramodularConnectivity")
+_PATCHED = ("pickSoftThreshold", "scaleFreeFitIndex", "calBlockSize", "checkSimilarity", "adjacency", "checkAdjMat",
+            "TOMsimilarity", "TomSimilarityFromAdj", "softConnectivity", "intramodularConnectivity")
 _saved = {}
 
 

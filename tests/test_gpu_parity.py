@@ -116,6 +116,12 @@ def test_check_adjmat(gpu):
         bw.checkAdjMat(A * 3)
     with pytest.raises(SystemExit):
         bw.TOMsimilarity(bad)
+    S = 2 * A - 1  # a similarity in [-1, 1]
+    bw.checkSimilarity(S)
+    with pytest.raises(SystemExit):
+        bw.checkSimilarity(S * 1.5)
+    with pytest.raises(SystemExit):
+        bw.checkSimilarity(bad)
     nan = bad.copy()
     nan[0, 1] = np.nan  # numpy: max/min are NaN -> both comparisons False -> passes
     bw.checkAdjMat(nan)
