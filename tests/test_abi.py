@@ -46,3 +46,33 @@ def test_fails_loudly_without_device():
     with pytest.raises(_lib.B200WError) as ei:
         bw.adjacency(np.random.default_rng(0).random((8, 12)))
     assert ei.value.code == _lib.E_NO_DEVICE
+
+
+def test_header_is_valid_c(tmp_path):
+    """include/b200wgcna.h is a plain C header (extern "C" ABI): it must compile as C99 and as C++."""
+    import subprocess
+
+    src = tmp_path / "t.c"
+    src.write_text('#include "b200wgcna.h"\nint main(void) { return B200W_VERSION == 100 ? 0 : 1; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(src)], check=True)
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", "-I", inc, str(src)], check=True)
+
+
+def test_argument_validation_returns_codes_not_crashes():
+    """Bad arguments are rejected with B200W_E_INVALID and a message before any device work."""
+    import numpy as np
+
+    lib = _lib.load()
+    x = np.zeros((4, 4))
+    out = np.zeros((4, 4))
+    rc = lib.b200w_adjacency(x.ctypes.data, 4, 4, 7, 6.0, 0, 4, out.ctypes.data, 0)  # bad network type or no device
+    assert rc in (_lib.E_INVALID, _lib.E_NO_DEVICE)
+    assert lib.b200w_adjacency(None, 4, 4, 0, 6.0, 0, 4, out.ctypes.data, 0) == _lib.E_INVALID
+    assert lib.b200w_adjacency(x.ctypes.data, 4, 4, 0, 6.0, 2, 4, out.ctypes.data, 0) == _lib.E_INVALID  # rows past n
+    assert lib.b200w_tom(x.ctypes.data, 0, 0, 0, 0, 0, 0, 0, out.ctypes.data, 0, None, 0) == _lib.E_INVALID
+    assert lib.b200w_connectivity_sweep(x.ctypes.data, 4, 4, None, 3, 0, out.ctypes.data, None, 0) == _lib.E_INVALID
+    assert b"bad args" in lib.b200w_last_error()
+    stats = np.zeros(4)
+    assert lib.b200w_check_adjacency(x.ctypes.data, -1, stats.ctypes.data, 0) == _lib.E_INVALID
+    assert lib.b200w_dev_tom_prepare(None, 4, 0, 4, 2, None, 128, None, None, 0, None) == _lib.E_INVALID
