@@ -122,6 +122,14 @@ int b200w_network(const double* X, int64_t m, int64_t n, int net_type, double po
                   int tom_denom, int out_mode, int precision, double* A_out, double* tom_out,
                   int device);
 
+/* Pearson correlation of every column of X (m x n) with every column of Y (m x M): the n x M block
+ * CalculateSignedKME takes out of np.corrcoef(datExpr.T, datME.T) (wgcna.py:3486-3489).  C_out n x M. */
+int b200w_cross_correlation(const double* X, int64_t m, int64_t n, const double* Y, int64_t M,
+                            double* C_out, int device);
+int b200w_dev_cross_correlation(const double* dZx, const uint8_t* d_badx, int64_t n, const double* dZy,
+                                const uint8_t* d_bady, int64_t M, int64_t m, double* dC, int device,
+                                void* stream);
+
 /* WGCNA.intramodularConnectivity, wgcna.py:3431-3445: diag <- 0, NaN -> 0, per-module
  * within-module row sums.  labels[n] are module ids in [0, nmod); small[nmod] != 0 marks
  * modules with < 3 genes (kWithin = 0, :3436).  out: kTotal[n], kWithin[n]. */

@@ -432,6 +432,33 @@ extern "C" int b200w_network(const double* X, int64_t m, int64_t n, int net_type
                                    n, tom_out, device, st.s);
 }
 
+extern "C" int b200w_cross_correlation(const double* X, int64_t m, int64_t n, const double* Y, int64_t M,
+                                       double* C_out, int device) {
+  if (!X || !Y || !C_out || m < 1 || n < 1 || M < 1) return fail(B200W_E_INVALID, "cross_correlation: bad args");
+  if (int e = ensure_device(device)) return e;
+  Stream st;
+  B200W_CUDA(st.create());
+  DevBuf dX, dY, dZx, dZy, dBx, dBy, dC;
+  const int64_t ldk = b200w_padded_k(m);
+  B200W_CUDA(dX.alloc((size_t)m * n * 8));
+  B200W_CUDA(dY.alloc((size_t)m * M * 8));
+  B200W_CUDA(dZx.alloc((size_t)n * ldk * 8));
+  B200W_CUDA(dZy.alloc((size_t)M * ldk * 8));
+  B200W_CUDA(dBx.alloc((size_t)n));
+  B200W_CUDA(dBy.alloc((size_t)M));
+  B200W_CUDA(dC.alloc((size_t)n * M * 8));
+  B200W_CUDA(cudaMemcpyAsync(dX.p, X, (size_t)m * n * 8, cudaMemcpyHostToDevice, st.s));
+  B200W_CUDA(cudaMemcpyAsync(dY.p, Y, (size_t)m * M * 8, cudaMemcpyHostToDevice, st.s));
+  if (int e = b200w_dev_standardize(dX.as<double>(), m, n, dZx.as<double>(), dBx.as<uint8_t>(), device, st.s)) return e;
+  if (int e = b200w_dev_standardize(dY.as<double>(), m, M, dZy.as<double>(), dBy.as<uint8_t>(), device, st.s)) return e;
+  if (int e = b200w_dev_cross_correlation(dZx.as<double>(), dBx.as<uint8_t>(), n, dZy.as<double>(), dBy.as<uint8_t>(),
+                                          M, m, dC.as<double>(), device, st.s))
+    return e;
+  B200W_CUDA(cudaMemcpyAsync(C_out, dC.p, (size_t)n * M * 8, cudaMemcpyDeviceToHost, st.s));
+  B200W_CUDA(cudaStreamSynchronize(st.s));
+  return 0;
+}
+
 extern "C" int b200w_intramodular(const double* A, int64_t n, const int32_t* labels, int nmod,
                                   const uint8_t* small, double* k_total, double* k_within,
                                   int device) {

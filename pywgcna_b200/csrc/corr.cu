@@ -310,9 +310,62 @@ adjacency_kernel(const double* __restrict__ Z, const uint8_t* __restrict__ bad, 
   }
 }
 
+// -------------------------------------------------------------------------------------------
+// Cross-correlation of two standardised gene sets, C[i, j] = cor(x_i, y_j): the n x M block that
+// CalculateSignedKME takes out of np.corrcoef(datExpr.T, datME.T) (wgcna.py:3486-3489) without forming
+// the (n + M)^2 matrix around it.  Same DMMA tile engine, epilogue clip + NaN rows/columns.
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGemmThreads, 1)
+cross_cor_kernel(const double* __restrict__ Zx, const uint8_t* __restrict__ badx, int64_t n,
+                 const double* __restrict__ Zy, const uint8_t* __restrict__ bady, int64_t M, int64_t ldk,
+                 double* __restrict__ C) {
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, tig = lane & 3;
+  const int64_t i0 = (int64_t)blockIdx.y * kBM, j0 = (int64_t)blockIdx.x * kBN;
+  AccF64 acc;
+  acc.clear();
+  gemm_f64_tile<kAdjStages>(acc, smem, Zx, Zy, ldk, ldk, i0, n, j0, M);
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      const int64_t gi = i0 + wm * 64 + mi * 16 + g + ch * 8;
+      if (gi >= n) continue;
+      const bool rbad = badx[gi];
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb) {
+          const int64_t gj = j0 + wn * 32 + ni * 8 + 2 * tig + cb;
+          if (gj >= M) continue;
+          double c = fmin(1.0, fmax(-1.0, acc.v[mi][ni][ch * 2 + cb]));
+          C[gi * M + gj] = (rbad || bady[gj]) ? qnan : c;
+        }
+    }
+}
+
 }  // namespace b200w
 
 using namespace b200w;
+
+extern "C" int b200w_dev_cross_correlation(const double* dZx, const uint8_t* d_badx, int64_t n,
+                                           const double* dZy, const uint8_t* d_bady, int64_t M, int64_t m,
+                                           double* dC, int device, void* stream) {
+  if (!dZx || !d_badx || !dZy || !d_bady || !dC || n < 1 || M < 1 || m < 1)
+    return fail(B200W_E_INVALID, "cross_correlation: bad args");
+  if (int e = ensure_device(device)) return e;
+  const size_t smem = gemm_smem_bytes(kAdjStages);
+  B200W_CUDA(cudaFuncSetAttribute(cross_cor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t rt = (n + kBM - 1) / kBM, ct = (M + kBN - 1) / kBN;
+  if (rt > 65535) return fail(B200W_E_UNSUPPORTED, "cross_correlation: too many row tiles");
+  dim3 grid((unsigned)ct, (unsigned)rt);
+  cross_cor_kernel<<<grid, kGemmThreads, smem, (cudaStream_t)stream>>>(dZx, d_badx, n, dZy, d_bady, M,
+                                                                      b200w_padded_k(m), dC);
+  B200W_LAUNCHED();
+  return 0;
+}
 
 extern "C" int64_t b200w_padded_k(int64_t m) { return round_up(m, kBK); }
 

@@ -607,6 +607,32 @@ def intramodularConnectivity(mat, colors, scaleByMax=False, index=None, device=N
     return res
 
 
+def signedKME(datExpr, datME, device=None):
+    """Eigengene-based connectivity (module membership): ``cor(gene, eigengene)`` for every gene and
+    module eigengene, the n x M block ``WGCNA.CalculateSignedKME`` slices out of
+    ``np.corrcoef(datExpr.T, datME.T)`` (wgcna.py:3486-3489) -- computed directly, without the
+    (n + M)^2 matrix.  Returns a DataFrame indexed by gene with columns ``"k" + eigengene name``."""
+    if datME.shape[0] != datExpr.shape[0]:
+        sys.exit("Number of samples (rows) in 'datExpr' and 'datME' must be the same.")  # :3462
+    X = L.as_f64_matrix(datExpr)
+    Y = L.as_f64_matrix(datME)
+    m, n = X.shape
+    M = Y.shape[1]
+    out = np.empty((n, M), dtype=np.float64)
+    L.check(L.load().b200w_cross_correlation(L.hptr(X), m, n, L.hptr(Y), M, L.hptr(out), _device(device)))
+    idx = datExpr.columns if hasattr(datExpr, "columns") else None
+    cols = ["k" + str(c) for c in (datME.columns if hasattr(datME, "columns") else range(M))]
+    return pd.DataFrame(out, index=idx, columns=cols)
+
+
+def CalculateSignedKME(self, exprWeights=None, MEWeights=None):
+    """Instance-method replacement of ``WGCNA.CalculateSignedKME`` (wgcna.py:3452-3490): fills
+    ``self.signedKME`` from ``self.datExpr`` / ``self.datME`` with the GPU cross-correlation."""
+    if exprWeights is not None or MEWeights is not None:
+        raise NotImplementedError("weights: np.corrcoef ignores them in the reference too")
+    self.signedKME = signedKME(self.datExpr.to_df(), self.datME)
+
+
 # ----------------------------------------------------------------------------------------------
 # drop-in installation
 # ----------------------------------------------------------------------------------------------
@@ -627,14 +653,21 @@ def install(target=None):
         if (target, name) not in _saved:
             _saved[(target, name)] = target.__dict__.get(name)
         setattr(target, name, staticmethod(g[name]))
+    if (target, "CalculateSignedKME") not in _saved:
+        _saved[(target, "CalculateSignedKME")] = target.__dict__.get("CalculateSignedKME")
+    target.CalculateSignedKME = CalculateSignedKME  # an instance method in the reference
     return target
 
 
 def uninstall(target=None):
     if target is None:
         from PyWGCNA.wgcna import WGCNA as target  # noqa: N811
-    for name in _PATCHED:
-        orig = _saved.pop((target, name), None)
+    for name in _PATCHED + ("CalculateSignedKME",):
+        if (target, name) not in _saved:
+            continue
+        orig = _saved.pop((target, name))
         if orig is not None:
             setattr(target, name, orig)
+        elif name in target.__dict__:
+            delattr(target, name)  # the class had no such attribute before install()
     return target

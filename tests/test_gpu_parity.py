@@ -358,3 +358,17 @@ def test_tiny_and_ragged_sizes(gpu, n, m):
     T0 = O.TOMsimilarity(A0.copy(), TOMType="unsigned").to_numpy()
     for prec in PRECISIONS:
         assert maxabs(bw.TOMsimilarity(A.copy(), TOMType="unsigned", precision=prec).to_numpy(), T0) < TOL_TOM[prec]
+
+
+def test_signed_kme(gpu):
+    """cor(gene, eigengene): the n x M block of np.corrcoef(datExpr.T, datME.T) (wgcna.py:3486-3489)."""
+    rng = np.random.default_rng(12)
+    X = make_expression(45, 700, F=5, seed=12)
+    X[:, 9] = 3.0  # constant gene -> NaN row
+    ME = pd.DataFrame(rng.standard_normal((45, 7)), columns=[f"ME{c}" for c in "abcdefg"])
+    df = pd.DataFrame(X, columns=[f"g{i}" for i in range(700)])
+    kme = bw.signedKME(df, ME)
+    with np.errstate(all="ignore"):
+        ref = np.corrcoef(X.T, ME.to_numpy().T)[:700, 700:]
+    assert list(kme.columns) == ["k" + c for c in ME.columns] and list(kme.index) == list(df.columns)
+    assert maxabs(kme.to_numpy(), ref) < 1e-12
