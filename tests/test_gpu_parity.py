@@ -372,3 +372,11 @@ def test_signed_kme(gpu):
         ref = np.corrcoef(X.T, ME.to_numpy().T)[:700, 700:]
     assert list(kme.columns) == ["k" + c for c in ME.columns] and list(kme.index) == list(df.columns)
     assert maxabs(kme.to_numpy(), ref) < 1e-12
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_tom_degenerate_sizes(gpu, prec):
+    for A in (np.array([[1.0]]), np.array([[1.0, 0.25], [0.25, 1.0]]), np.zeros((4, 4))):
+        T = bw.TOMsimilarity(A.copy(), TOMType="unsigned", precision=prec).to_numpy()
+        T0 = O.TOMsimilarity(A.copy(), TOMType="unsigned").to_numpy()
+        assert maxabs(T, T0) < 1e-15
