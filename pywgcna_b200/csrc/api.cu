@@ -50,6 +50,15 @@ int ensure_device(int device) {
       if (cudaDeviceGetAttribute(&mj, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess)
         return fail(B200W_E_CUDA, "cannot query device %d", device);
       major_of[device] = mj;
+      // keep stream-ordered scratch (cudaMallocAsync in the dev_* calls) in the pool across
+      // synchronisations: with the default release threshold of 0 every sync hands the memory back to
+      // the driver and the next call pays for mapping it again (bimodal 53 / 90 ms bench steps)
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      cudaGetLastError();
     }
     if (major_of[device] != 10)
       return fail(B200W_E_NO_DEVICE, "device %d is sm_%dx; this library is built for sm_100a only",

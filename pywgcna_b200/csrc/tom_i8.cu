@@ -36,7 +36,7 @@ constexpr int kS = B200W_I8_SLICES;  // digit planes stored
 constexpr int kFixBits = 8 * kS - 2;  // 38
 constexpr int kTM = 128, kTN = 256, kKB = 128;  // tile rows, tile cols, K bytes per stage
 constexpr int kMaxSegs = 96, kMaxPasses = 48;
-constexpr int kI8Threads = 256;
+constexpr int kI8Threads = 320;  // warps: 0 TMA, 1 MMA, 2-3 + 8-9 finalizers (2 also owns TMEM), 4-7 epilogue
 constexpr int kMaxKbPerPass = 1023;
 
 struct Seg {
@@ -61,6 +61,7 @@ struct I8Params {
   double* peer_out[8];    // ... and is stored into that rank's row block (peer HBM over NVLink)
   int32_t nseg, npass;
   int32_t tom_type, tom_denom, out_mode, group;
+  int32_t fin_warps;       // finalizer warps per CTA: 4 (warps 2, 3, 8, 9; measured best) or 2 (warps 2, 3)
   int32_t sync_mode;       // 0 none, 1 grid barrier of the producers per tile, 2 per segment
   unsigned int* sync_ctr;  // zeroed before launch
   double final_scale;    // 256^w_min
@@ -320,7 +321,7 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
       mbar_init(&bars->tmem_full[a], 1);
       mbar_init(&bars->tmem_empty[a], 4 * kCtas);  // one arrive per epilogue warp of every CTA
       mbar_init(&bars->fin_full[a], 4);            // the 4 epilogue warps of this CTA
-      mbar_init(&bars->fin_empty[a], 2);           // the 2 finalizer warps of this CTA
+      mbar_init(&bars->fin_empty[a], p.fin_warps);  // the finalizer warps of this CTA
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -463,7 +464,7 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     // ================ epilogue: TMEM accumulator -> float64 running sum in scratch ===============
     // Every pass is drained at once (coalesced scratch, lanes = rows) and the accumulator handed back
     // to the MMA warp.  The TOM formula and the n x n stores are NOT done here: measured at C2, doing
@@ -510,13 +511,15 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
       if (lane == 0) mbar_arrive(&bars->fin_full[buf]);  // release: the sums of this tile are in scratch
       ++done;
     }
-  } else {
-    // ====== finalizers (warps 2 and 3): TOM formula + stores of a finished tile, off the MMA path ======
+  } else if (warp - (warp < 4 ? 2 : 6) < p.fin_warps) {
+    // ====== finalizers (warps 2, 3, 8, 9; 8 warps measured no better than 4, 2 warps 6 % slower): TOM formula + stores of a finished tile, off the MMA path ======
     // symmetric schedule: TOM_ji = TOM_ij, stored from the same registers; for a fixed column the 32
     // lanes of a warp hold 32 consecutive rows, so the mirrored store is one coalesced 256-byte line
     // (in a diagonal tile only the entries on and above the diagonal are stored, with their mirror);
     // the mirrored row gj may belong to another GPU: the store then goes to that GPU's HBM
-    const int f = warp - 2;
+    const int f = warp < 4 ? warp - 2 : warp - 6;  // warps 2, 3, 8, 9 -> finalizer 0..3
+    const int nslab = p.fin_warps == 4 ? 1 : 2;  // 32-row slabs per finalizer
+    const int slab0 = f * nslab;
     const bool mirror = p.symmetric != 0;
     int64_t done = 0;
     for (int64_t it = 0; it < iters; ++it) {
@@ -535,7 +538,7 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
       // predicated.  (With the loads inside the per-element branch this loop ran ~3700 cycles per element
       // and throttled the whole kernel through the scratch hand-off.)
 #pragma unroll 1
-      for (int slab = 2 * f; slab < 2 * f + 2; ++slab) {
+      for (int slab = slab0; slab < slab0 + nslab; ++slab) {
         const int row = slab * 32 + lane;
         const int64_t gi = p.tile_row_base + tm * Cfg::kTileRows + rank * kTM + row;
         const bool row_ok = gi < p.row0 + p.nrows;
@@ -792,6 +795,8 @@ int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t o
   Scratch scratch;
   B200W_CUDA(scratch.alloc((size_t)grid * 2 * kTM * kTN * sizeof(double), st));  // two tiles per CTA
   prm.scratch = scratch.as<double>();
+  prm.fin_warps = 4;
+  if (const char* e = getenv("B200W_I8_FIN")) prm.fin_warps = atoi(e) == 2 ? 2 : 4;
   prm.sync_mode = 3;
   if (const char* e = getenv("B200W_I8_SYNC")) prm.sync_mode = atoi(e);
   Scratch ctr;
