@@ -144,6 +144,9 @@ int b200w_intramodular(const double* A, int64_t n, const int32_t* labels, int nm
 void* b200w_host_alloc(int64_t bytes);
 void b200w_host_free(void* p);
 void b200w_host_trim(void);
+/* The host entry points keep their multi-GB device workspaces (adjacency, operand, result) cached
+ * between calls instead of cudaMalloc / cudaFree each time; this releases the cached ones. */
+void b200w_dev_trim(void);
 
 /* ---------------------------------------------------------------- device entry points */
 

@@ -54,7 +54,7 @@ int ensure_device(int device) {
       // synchronisations: with the default release threshold of 0 every sync hands the memory back to
       // the driver and the next call pays for mapping it again (bimodal 53 / 90 ms bench steps)
       cudaMemPool_t pool;
-      if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      if (!getenv("B200W_POOL_RELEASE") && cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t keep = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
       }
@@ -68,12 +68,80 @@ int ensure_device(int device) {
   return 0;
 }
 
+// Device workspace of the host entry points.  cudaMalloc / cudaFree of the multi-GB buffers (adjacency,
+// operand, result) cost tens to hundreds of ms per call and synchronise the device, so freed buffers are
+// kept per device and handed out again (smallest cached buffer of at least the requested size and at most
+// 25 % larger).  b200w_dev_trim() gives everything back; at most 70 % of the device memory is cached.
+struct DevCache {
+  std::mutex mu;
+  struct Item { int dev; size_t bytes; void* p; };
+  std::vector<Item> free_;
+  std::map<void*, std::pair<int, size_t>> live;
+  size_t cached = 0;
+  cudaError_t get(size_t bytes, void** out) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      int best = -1;
+      for (int i = 0; i < (int)free_.size(); ++i)
+        if (free_[i].dev == dev && free_[i].bytes >= bytes && free_[i].bytes <= bytes + bytes / 4 + 4096 &&
+            (best < 0 || free_[i].bytes < free_[best].bytes))
+          best = i;
+      if (best >= 0) {
+        *out = free_[best].p;
+        live[*out] = {dev, free_[best].bytes};
+        cached -= free_[best].bytes;
+        free_.erase(free_.begin() + best);
+        return cudaSuccess;
+      }
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e == cudaErrorMemoryAllocation) {  // make room and retry once
+      cudaGetLastError();
+      trim();
+      e = cudaMalloc(out, bytes);
+    }
+    if (e == cudaSuccess) {
+      std::lock_guard<std::mutex> lk(mu);
+      live[*out] = {dev, bytes};
+    }
+    return e;
+  }
+  void put(void* p) {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = live.find(p);
+    if (it == live.end()) {
+      cudaFree(p);
+      return;
+    }
+    const int dev = it->second.first;
+    const size_t bytes = it->second.second;
+    live.erase(it);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    if (bytes < ((size_t)1 << 20) || cached + bytes > total_b / 10 * 7) {
+      cudaFree(p);
+    } else {
+      free_.push_back({dev, bytes, p});
+      cached += bytes;
+    }
+  }
+  void trim() {
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& f : free_) cudaFree(f.p);
+    free_.clear();
+    cached = 0;
+  }
+};
+static DevCache g_dev_cache;
+
 // RAII device buffer + stream for the host entry points
 struct DevBuf {
   void* p = nullptr;
-  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+  cudaError_t alloc(size_t bytes) { return g_dev_cache.get(bytes ? bytes : 16, &p); }
   ~DevBuf() {
-    if (p) cudaFree(p);
+    if (p) g_dev_cache.put(p);
   }
   template <class T>
   T* as() const {
@@ -222,6 +290,7 @@ extern "C" int b200w_ipc_close(void* p, int device) {
 extern "C" void* b200w_host_alloc(int64_t bytes) { return bytes < 0 ? nullptr : g_pool.alloc((size_t)bytes); }
 extern "C" void b200w_host_free(void* p) { g_pool.free(p); }
 extern "C" void b200w_host_trim(void) { g_pool.trim(); }
+extern "C" void b200w_dev_trim(void) { g_dev_cache.trim(); }
 
 int b200w_dev_intramodular(const double* dA, int64_t n, const int32_t* d_labels,
                            const uint8_t* d_small, double* d_total, double* d_within,
