@@ -380,3 +380,19 @@ def test_tom_degenerate_sizes(gpu, prec):
         T = bw.TOMsimilarity(A.copy(), TOMType="unsigned", precision=prec).to_numpy()
         T0 = O.TOMsimilarity(A.copy(), TOMType="unsigned").to_numpy()
         assert maxabs(T, T0) < 1e-15
+
+
+@pytest.mark.parametrize("env", [{"B200W_I8_CTAS": "1"}, {"B200W_I8_SYMMETRIC": "0"}, {"B200W_I8_FIN": "2"},
+                                 {"B200W_I8_SYNC": "0"}, {"B200W_I8_NOCOOP": "1"}, {"B200W_I8_WMIN": "3"}])
+def test_int8_kernel_variants(gpu, env, monkeypatch):
+    """The schedule knobs of the tcgen05 kernel (1-CTA tiles, full instead of symmetric schedule, two
+    finalizer warps, no producer barrier, non-cooperative launch as used under ncu, one more digit-pair
+    class) change speed, never the result beyond its tolerance."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    n = 777
+    X = make_expression(50, n, F=5, seed=n)
+    A = O.adjacency(X, adjacencyType="unsigned", power=6)
+    T_ref = O.TOMsimilarity(A.copy(), TOMType="unsigned").to_numpy()
+    T = bw.TOMsimilarity(A.copy(), TOMType="unsigned", precision="i8").to_numpy()
+    assert maxabs(T, T_ref) < TOL_TOM["i8"]
