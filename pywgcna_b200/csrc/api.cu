@@ -10,7 +10,12 @@
 #include <thread>
 #include <vector>
 
-#include "common.cuh"
+#include "tom_common.cuh"
+
+int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t op_rows, const double* d_scale,
+                         const double* d_k, int64_t n, int64_t row0, int64_t nrows, int tom_type, int tom_denom,
+                         int out_mode, double* d_out, cudaStream_t st, int world, int rank, int64_t per,
+                         double* const* peer_out, b200w::TomProgress* progress);
 
 namespace b200w {
 
@@ -438,6 +443,38 @@ static int tom_from_device_adjacency(const double* dA, int64_t n, int tom_type, 
   if (int e = b200w_dev_tom_prepare(dA, n, 0, n, precision, dOp.p, op_rows, dScale.as<double>(),
                                     dK.as<double>(), device, s))
     return e;
+  if (precision == B200W_PREC_I8 && row0 == 0 && nrows == n && !condensed && !getenv("B200W_NO_OVERLAP")) {
+    // whole matrix on the tensor-core path: the kernel reports finished row blocks through host-mapped
+    // flags and they are copied out on a second stream while later blocks are still being computed
+    // (3.2 GB of D2H at C2 take 62 ms, the kernel 35 ms: the copy hides the kernel, not the reverse)
+    if (tom_type < 0 || tom_type > 1 || tom_denom < 0 || tom_denom > 1 || out_mode < 0 || out_mode > 2)
+      return fail(B200W_E_INVALID, "tom: bad enum");
+    TomProgress prog;
+    if (int e = b200w_tom_compute_i8(dA, dOp.p, op_rows, dScale.as<double>(), dK.as<double>(), n, 0, n, tom_type,
+                                     tom_denom, out_mode, dOut.as<double>(), s, 1, 0, 0, nullptr, &prog))
+      return e;
+    if (prog.nb > 0) {
+      Stream s2;
+      B200W_CUDA(s2.create());
+      for (int b = 0; b < prog.nb; ++b) {
+        unsigned long long spins = 0;
+        while (prog.flags[b] == 0u) {
+          if ((++spins & 0xfff) == 0 && cudaStreamQuery(s) != cudaErrorNotReady) break;  // kernel over (or failed)
+        }
+        const int64_t r0 = (int64_t)b * prog.rows_per_block;
+        const int64_t r1 = r0 + prog.rows_per_block < n ? r0 + prog.rows_per_block : n;
+        if (r1 > r0)
+          B200W_CUDA(cudaMemcpyAsync(out_host + r0 * n, dOut.as<double>() + r0 * n, (size_t)(r1 - r0) * n * 8,
+                                     cudaMemcpyDeviceToHost, s2.s));
+      }
+      B200W_CUDA(cudaStreamSynchronize(s));  // surfaces a kernel failure; all flags were set if it succeeded
+      B200W_CUDA(cudaStreamSynchronize(s2.s));
+      return 0;
+    }
+    B200W_CUDA(cudaMemcpyAsync(out_host, dOut.p, out_bytes, cudaMemcpyDeviceToHost, s));
+    B200W_CUDA(cudaStreamSynchronize(s));
+    return 0;
+  }
   if (int e = b200w_dev_tom_compute(dA + row0 * n, dOp.p, op_rows, dScale.as<double>(),
                                     dK.as<double>(), n, row0, nrows, tom_type, tom_denom, out_mode, precision,
                                     dOut.as<double>(), device, s))

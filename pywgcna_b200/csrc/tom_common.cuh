@@ -4,6 +4,14 @@
 
 namespace b200w {
 
+// progress of a whole-matrix symmetric TOM launch, for a host that copies finished row blocks out while
+// the kernel is still running: flags[b] (host-mapped) becomes 1 when rows [b, b + 1) * rows_per_block are final
+struct TomProgress {
+  volatile unsigned int* flags = nullptr;
+  int nb = 0;
+  int64_t rows_per_block = 0;
+};
+
 #ifdef __CUDACC__
 // np.nan_to_num (wgcna.py:1185; default also maps +-inf to +-DBL_MAX, unreachable for a matrix that
 // passed checkAdjMat) and fill_diagonal(A, 0) (wgcna.py:1143)

@@ -61,6 +61,10 @@ struct I8Params {
   double* peer_out[8];    // ... and is stored into that rank's row block (peer HBM over NVLink)
   int32_t nseg, npass;
   int32_t tom_type, tom_denom, out_mode, group;
+  unsigned int* prog_count;           // optional: per row block, finalizer warps that finished a tile touching it
+  const unsigned int* prog_expected;  //           value of prog_count at which the block's rows are complete
+  unsigned int* prog_flag;            //           host-mapped flags, set to 1 when a block is complete
+  int32_t prog_tiles;                 //           row tiles (of 256 rows) per row block
   int32_t fin_warps;       // finalizer warps per CTA: 4 (warps 2, 3, 8, 9; measured best) or 2 (warps 2, 3)
   int32_t sync_mode;       // 0 none, 1 grid barrier of the producers per tile, 2 per segment
   unsigned int* sync_ctr;  // zeroed before launch
@@ -585,6 +589,24 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
           }
         }
       }
+      if (p.prog_count != nullptr) {
+        // progress for the host: when every finalizer warp of every tile that touches a row block has
+        // passed here, the block's rows are final and the host starts copying them out while the rest of
+        // the kernel is still running
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0) {
+          const int b0 = (int)(tm / p.prog_tiles), b1 = (int)(tn / p.prog_tiles);
+          for (int b = b0;; b = b1) {
+            const unsigned int old = atomicAdd(&p.prog_count[b], 1u);
+            if (old + 1 == p.prog_expected[b]) {
+              __threadfence_system();
+              *(volatile unsigned int*)&p.prog_flag[b] = 1u;
+            }
+            if (b == b1) break;
+          }
+        }
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->fin_empty[buf]);
       ++done;
@@ -683,7 +705,7 @@ int b200w_tom_prepare_i8(const double* dA_rows, int64_t n, int64_t row0, int64_t
 int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t op_rows, const double* d_scale,
                          const double* d_k, int64_t n, int64_t row0, int64_t nrows, int tom_type, int tom_denom,
                          int out_mode, double* d_out, cudaStream_t st, int world, int rank, int64_t per,
-                         double* const* peer_out) {
+                         double* const* peer_out, b200w::TomProgress* progress) {
   const int64_t ldn = b200w_padded_n(n);
   if (op_rows > 0x7fffffff || ldn > 0x7fffffff) return fail(B200W_E_UNSUPPORTED, "tom_i8: n too large");
   EncodeTiledFn encode = get_encode_tiled();
@@ -771,8 +793,10 @@ int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t o
         return false;
       });
     } else if (symmetric) {
-      for (int bn = 0; bn * G < TN; ++bn)
-        for (int bm = 0; bm <= bn; ++bm)
+      // row-major over the super-blocks: when the block row bm is finished, rows [bm G 256, (bm+1) G 256)
+      // are final (their direct tiles belong to this block row, their mirrored tiles to earlier ones)
+      for (int bm = 0; bm * G < TM; ++bm)
+        for (int bn = bm; bn * G < TN; ++bn)
           for (int tn = bn * G; tn < TN && tn < (bn + 1) * G; ++tn)
             for (int tm = bm * G; tm < TM && tm < (bm + 1) * G; ++tm)
               if (tm <= tn) tiles.push_back(make_int2(tm, tn));
@@ -795,10 +819,49 @@ int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t o
   Scratch scratch;
   B200W_CUDA(scratch.alloc((size_t)grid * 2 * kTM * kTN * sizeof(double), st));  // two tiles per CTA
   prm.scratch = scratch.as<double>();
+  prm.prog_count = nullptr;
+  prm.prog_expected = nullptr;
+  prm.prog_flag = nullptr;
+  prm.prog_tiles = prm.group > 0 ? prm.group : 8;
   prm.fin_warps = 4;
   if (const char* e = getenv("B200W_I8_FIN")) prm.fin_warps = atoi(e) == 2 ? 2 : 4;
   prm.sync_mode = 3;
   if (const char* e = getenv("B200W_I8_SYNC")) prm.sync_mode = atoi(e);
+  if (progress != nullptr) {
+    progress->nb = 0;
+    if (symmetric && !dist && !out_is_condensed(out_mode)) {
+      // expected finalizer-warp arrivals per row block = (warps per tile over the CTA pair) x (tiles that
+      // touch the block through their direct rows tm or their mirrored rows tn)
+      static unsigned int* h_flags = nullptr;  // host-mapped, 1024 blocks
+      static unsigned int *d_flags = nullptr, *d_counts = nullptr, *d_expected = nullptr;
+      if (!h_flags) {
+        B200W_CUDA(cudaHostAlloc((void**)&h_flags, 1024 * sizeof(unsigned int), cudaHostAllocMapped));
+        B200W_CUDA(cudaHostGetDevicePointer((void**)&d_flags, h_flags, 0));
+        B200W_CUDA(cudaMalloc(&d_counts, 1024 * sizeof(unsigned int)));
+        B200W_CUDA(cudaMalloc(&d_expected, 1024 * sizeof(unsigned int)));
+      }
+      const int Gp = prm.prog_tiles, nb = (prm.tiles_m + Gp - 1) / Gp;
+      if (nb <= 1024) {
+        std::vector<unsigned int> expect(nb, 0u);
+        const unsigned int per_tile = (unsigned int)prm.fin_warps * 2u;
+        for (int tm = 0; tm < prm.tiles_m; ++tm)
+          for (int tn = tm; tn < prm.tiles_n; ++tn) {
+            expect[tm / Gp] += per_tile;
+            if (tn / Gp != tm / Gp) expect[tn / Gp] += per_tile;
+          }
+        for (int b = 0; b < nb; ++b) h_flags[b] = 0u;
+        B200W_CUDA(cudaMemsetAsync(d_counts, 0, nb * sizeof(unsigned int), st));
+        B200W_CUDA(cudaMemcpyAsync(d_expected, expect.data(), nb * sizeof(unsigned int), cudaMemcpyHostToDevice, st));
+        B200W_CUDA(cudaStreamSynchronize(st));  // `expect` is pageable and local
+        prm.prog_count = d_counts;
+        prm.prog_expected = d_expected;
+        prm.prog_flag = d_flags;
+        progress->flags = h_flags;
+        progress->nb = nb;
+        progress->rows_per_block = (int64_t)Gp * 256;
+      }
+    }
+  }
   Scratch ctr;
   B200W_CUDA(ctr.alloc(64, st));
   B200W_CUDA(cudaMemsetAsync(ctr.p, 0, 64, st));
