@@ -59,23 +59,60 @@ standardize_kernel(const double* __restrict__ X, int64_t m, int64_t n, int64_t l
   }
 }
 // -------------------------------------------------------------------------------------------
-// K2  fused soft-threshold sweep.  The work is the CT x RT grid of 128 x 128 correlation tiles
+// Both kernels below use the narrow engine (gemm_f64.cuh: 128 x 64 tile, 4 warps, two CTAs per SM) and
+// hand the finished tile from the accumulator registers to the epilogue through the -- by then idle --
+// operand ring: each warp parks its own 64 x 32 sub-tile there and re-reads it with lane <-> column.
+// That frees the 128 accumulator registers, turns the epilogue into short rolled loops (the unrolled
+// register-indexed form was instruction-fetch bound in the adjacency and shuffle-latency bound in the
+// sweep) and makes every global store a 256-byte row segment.
+// -------------------------------------------------------------------------------------------
+using Narrow = GemmCfg<2>;
+constexpr int kNarrowBN = Narrow::kBNt, kNarrowThreads = Narrow::kThreads;
+
+// park the warp's 64 x 32 accumulator sub-tile at wt[row * kPitch + col]
+template <int kPitch>
+__device__ __forceinline__ void park_acc(const AccF64& acc, double* wt, int lane) {
+  const int g = lane >> 2, tig = lane & 3;
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        double* p = wt + (mi * 16 + ch * 8 + g) * kPitch + ni * 8 + 2 * tig;
+        if (kPitch % 2 == 0) {
+          *reinterpret_cast<double2*>(p) = make_double2(acc.v[mi][ni][ch * 2], acc.v[mi][ni][ch * 2 + 1]);
+        } else {
+          p[0] = acc.v[mi][ni][ch * 2];
+          p[1] = acc.v[mi][ni][ch * 2 + 1];
+        }
+      }
+  __syncwarp();
+}
+
+// -------------------------------------------------------------------------------------------
+// K2  fused soft-threshold sweep.  The work is the CT x RT grid of 128 x 64 correlation tiles
 // (CT column tiles of the genes whose connectivity is wanted, RT row tiles of all genes), taken
-// column-major and cut into one contiguous, equally long range per CTA (persistent, one CTA per SM:
-// no tail wave).  For each tile the CTA computes Z_i Z_j^T on the DMMA pipe and, while the tile is
-// still in registers, evaluates clip -> similarity transform -> diag <- 1 -> NaN skip -> the running
-// product chain for all P powers, reducing over rows.  The n x n matrix is never written.
-// Column sums accumulate in shared memory with exactly one owner lane per (warp row, power, column);
-// whenever the range crosses into the next column tile the sums are flushed to a partial slot, and
-// sweep_reduce_kernel adds the slots of a column tile in CTA order: deterministic, no atomics.
-//
-// Epilogue shape: a quarter of the warp's 64 x 32 sub-tile (8 columns = 2 per thread, 8 rows each) is
-// processed at a time; the transformed similarities overwrite the accumulator registers, the 16
-// running products live in registers, and per power the 2 column sums go through tree adds and
-// three shuffle rounds together, so their latencies overlap.
+// column-major and cut into one contiguous, equally long range per CTA (persistent, two CTAs per SM:
+// no tail wave).  For each tile the CTA computes Z_i Z_j^T on the DMMA pipe and evaluates
+// clip -> similarity transform -> diag <- 1 -> NaN skip -> the running product chain for all P powers,
+// reducing over rows.  The n x n matrix is never written.
+// Epilogue: a lane owns one column of the warp's sub-tile and walks its 64 rows four at a time; when every
+// step of the chain is 1 or 2 (the reference's default list, and any list of consecutive or even powers)
+// the P running column sums stay in registers for the whole tile -- one DMUL + one DADD per element and
+// power, no shuffles; other step lists go through a rolled loop with pow() and shared-memory sums.
+// Column sums of a column tile accumulate in shared memory with exactly one owner thread per
+// (warp row, power, column); whenever the range crosses into the next column tile the sums are flushed to
+// a partial slot, and sweep_reduce_kernel adds the slots of a column tile in CTA order: deterministic,
+// no atomics.
 // -------------------------------------------------------------------------------------------
 constexpr int kSweepStages = 3;
-constexpr int kSweepMaxP = 32;
+constexpr int kSweepMaxP = 20;   // 3 ring slots + 2 x 20 x 64 sums: two CTAs fit one SM
+constexpr int kSweepPitch = 40;  // doubles; conflict-free 16-byte parking stores
+#ifndef B200W_SWEEP_ROWS
+#define B200W_SWEEP_ROWS 8
+#endif
+constexpr int kSweepRows = B200W_SWEEP_ROWS;  // rows of a column in flight per lane: independent chains
 
 struct SweepParams {
   const double* Z;
@@ -86,7 +123,8 @@ struct SweepParams {
   int P;
   int net_type;
   int max_seg;          // partial slots per CTA
-  double* partial;      // [gridDim.x][max_seg][P][128]
+  int simple_steps;     // every istep is 1 or 2
+  double* partial;      // [gridDim.x][max_seg][P][64]
   double step[kSweepMaxP];
   int istep[kSweepMaxP];
 };
@@ -96,13 +134,15 @@ __device__ __forceinline__ void sweep_range(int64_t T, int64_t G, int64_t b, int
   t1 = T * (b + 1) / G;
 }
 
-__global__ void __launch_bounds__(kGemmThreads, 1) sweep_kernel(const SweepParams prm) {
+__global__ void __launch_bounds__(kNarrowThreads, 2) sweep_kernel(const SweepParams prm) {
+  constexpr int kBN = kNarrowBN;
   extern __shared__ __align__(16) double smem[];
-  double* colacc = smem + kSweepStages * kStageDoubles;  // [2][P][128]
+  double* colacc = smem + kSweepStages * Narrow::kSlotDoubles;  // [2][P][64]
   __shared__ uint8_t bad_col[kBN], bad_row[kBM];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, tig = lane & 3;
+  const int wm = warp >> 1, wn = warp & 1;
+  double* wt = smem + warp * 64 * kSweepPitch;  // this warp's parking space inside the ring
   const int P = prm.P;
   const int64_t n = prm.n;
   const int64_t jend = prm.col0 + prm.ncols;
@@ -115,91 +155,96 @@ __global__ void __launch_bounds__(kGemmThreads, 1) sweep_kernel(const SweepParam
   for (int64_t t = t0; t < t1; ++t) {
     const int64_t jt = t / prm.RT, it = t - jt * prm.RT;
     const int64_t j0 = prm.col0 + jt * kBN, i0 = it * kBM;
+    __syncthreads();  // every warp is done with the parked tile, bad_row and (on a flush) the sums
     if (jt != cur_jt) {  // entering a new column tile: flush the previous one, reset the sums
-      __syncthreads();
       if (cur_jt >= 0) {
         double* dst = prm.partial + ((int64_t)blockIdx.x * prm.max_seg + (cur_jt - jt_first)) * P * kBN;
-        for (int i = threadIdx.x; i < P * kBN; i += kGemmThreads) dst[i] = colacc[i] + colacc[P * kBN + i];
+        for (int i = threadIdx.x; i < P * kBN; i += kNarrowThreads) dst[i] = colacc[i] + colacc[P * kBN + i];
         __syncthreads();
       }
-      for (int i = threadIdx.x; i < 2 * P * kBN; i += kGemmThreads) colacc[i] = 0.0;
+      for (int i = threadIdx.x; i < 2 * P * kBN; i += kNarrowThreads) colacc[i] = 0.0;
       if (threadIdx.x < kBN) {
         int64_t j = j0 + threadIdx.x;
         bad_col[threadIdx.x] = (j < jend) ? prm.bad[j] : 1;
       }
       cur_jt = jt;
     }
-    if (threadIdx.x < kBM) {
-      int64_t i = i0 + threadIdx.x;
+    {
+      int64_t i = i0 + threadIdx.x;  // 128 threads = 128 rows
       bad_row[threadIdx.x] = (i < n) ? prm.bad[i] : 1;
     }
-    AccF64 acc;
-    acc.clear();
-    // rows of the tile = genes i (summed over), columns = genes j (kept)
-    gemm_f64_tile<kSweepStages>(acc, smem, prm.Z, prm.Z, prm.ldk, prm.ldk, i0, n, j0, n);
-    // (gemm_f64_tile ends with a __syncthreads, so bad_row / bad_col / the zeroed sums are visible)
+    {
+      AccF64 acc;
+      acc.clear();
+      // rows of the tile = genes i (summed over), columns = genes j (kept)
+      gemm_f64_tile<kSweepStages, 2>(acc, smem, prm.Z, prm.Z, prm.ldk, prm.ldk, i0, n, j0, n);
+      // (ends with a __syncthreads: the ring is idle, bad_row / bad_col / the zeroed sums are visible)
+      park_acc<kSweepPitch>(acc, wt, lane);
+    }
 
+    const int col = wn * 32 + lane;
+    const int64_t gj = j0 + col;
+    const bool cbad = bad_col[col];
+    double* mysum = colacc + (size_t)wm * P * kBN + col;  // [p * kBN]: this thread's own sums
+
+    // similarity and chain start of one element: wgcna.py:884-897, NaN skipped by nansum (:915)
+    auto load = [&](int r, double& sv, double& c0) {
+      const int row = wm * 64 + r;
+      const int64_t gi = i0 + row;
+      double c = wt[r * kSweepPitch + lane];
+      c = fmin(1.0, fmax(-1.0, c));  // np.corrcoef clips to [-1, 1]
+      sv = net_transform(c, prm.net_type);
+      c0 = 1.0;
+      if (gi == gj) sv = 1.0;  // wgcna.py:897 (even for a NaN gene)
+      else if (cbad || bad_row[row]) { sv = 0.0; c0 = 0.0; }
+      if (gi >= n) { sv = 0.0; c0 = 0.0; }
+    };
+
+    if (prm.simple_steps) {
+      double ks[kSweepMaxP];
 #pragma unroll
-    for (int ni = 0; ni < 4; ++ni) {
-      double cur[16];
-      // element e = (cb * 4 + mi) * 2 + ch  ->  acc.v[mi][ni][ch * 2 + cb]
-#pragma unroll
-      for (int cb = 0; cb < 2; ++cb) {
-        const int col = wn * 32 + ni * 8 + 2 * tig + cb;
-        const int64_t gj = j0 + col;
-        const bool cbad = bad_col[col];
-#pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-          for (int ch = 0; ch < 2; ++ch) {
-            const int row = wm * 64 + mi * 16 + g + ch * 8;
-            const int64_t gi = i0 + row;
-            double c = acc.v[mi][ni][ch * 2 + cb];
-            c = fmin(1.0, fmax(-1.0, c));                // np.corrcoef clips to [-1, 1]
-            double sv = net_transform(c, prm.net_type);  // wgcna.py:884-889
-            double c0 = 1.0;
-            if (gi == gj) sv = 1.0;                      // wgcna.py:897 (even for a NaN gene)
-            else if (cbad || bad_row[row]) { sv = 0.0; c0 = 0.0; }  // NaN: skipped by nansum :915
-            if (gi >= n) { sv = 0.0; c0 = 0.0; }
-            acc.v[mi][ni][ch * 2 + cb] = sv;
-            cur[(cb * 4 + mi) * 2 + ch] = c0;
-          }
-      }
+      for (int p = 0; p < kSweepMaxP; ++p) ks[p] = 0.0;
 #pragma unroll 1
-      for (int p = 0; p < P; ++p) {
-        const int ist = prm.istep[p];
-        // wgcna.py:914  corxCur = corxPrev * corx ** step
-        if (ist == 1) {
+      for (int r0 = 0; r0 < 64; r0 += kSweepRows) {
+        double s1[kSweepRows], s2[kSweepRows], cur[kSweepRows];
 #pragma unroll
-          for (int cb = 0; cb < 2; ++cb)
+        for (int u = 0; u < kSweepRows; ++u) {
+          load(r0 + u, s1[u], cur[u]);
+          s2[u] = s1[u] * s1[u];
+        }
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
+        for (int p = 0; p < kSweepMaxP; ++p) {
+          if (p < P) {  // wgcna.py:914  corxCur = corxPrev * corx ** step
+            const bool one = prm.istep[p] == 1;
 #pragma unroll
-              for (int ch = 0; ch < 2; ++ch) cur[(cb * 4 + mi) * 2 + ch] *= acc.v[mi][ni][ch * 2 + cb];
-        } else {
+            for (int u = 0; u < kSweepRows; ++u) cur[u] *= one ? s1[u] : s2[u];
+            double part[kSweepRows / 4];
+#pragma unroll
+            for (int q = 0; q < kSweepRows / 4; ++q)
+              part[q] = (cur[4 * q] + cur[4 * q + 1]) + (cur[4 * q + 2] + cur[4 * q + 3]);
+            double tot = part[0];
+#pragma unroll
+            for (int q = 1; q < kSweepRows / 4; ++q) tot += part[q];
+            ks[p] += tot;
+          }
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < kSweepMaxP; ++p)
+        if (p < P) mysum[p * kBN] += ks[p];
+    } else {
+#pragma unroll 1
+      for (int r0 = 0; r0 < 64; r0 += 4) {
+        double s1[4], cur[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) load(r0 + u, s1[u], cur[u]);
+#pragma unroll 1
+        for (int p = 0; p < P; ++p) {
           const double st = prm.step[p];
+          const int ist = prm.istep[p];
 #pragma unroll
-          for (int cb = 0; cb < 2; ++cb)
-#pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-              for (int ch = 0; ch < 2; ++ch)
-                cur[(cb * 4 + mi) * 2 + ch] *= step_pow(acc.v[mi][ni][ch * 2 + cb], st, ist);
-        }
-        double v[2];
-#pragma unroll
-        for (int cb = 0; cb < 2; ++cb) {
-          const double* q = cur + cb * 8;
-          v[cb] = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
-        }
-#pragma unroll
-        for (int o = 4; o <= 16; o <<= 1)
-#pragma unroll
-          for (int cb = 0; cb < 2; ++cb) v[cb] += __shfl_xor_sync(0xffffffffu, v[cb], o);
-        if (g == 0) {
-#pragma unroll
-          for (int cb = 0; cb < 2; ++cb)
-            colacc[(wm * P + p) * kBN + wn * 32 + ni * 8 + 2 * tig + cb] += v[cb];
+          for (int u = 0; u < 4; ++u) cur[u] *= step_pow(s1[u], st, ist);
+          mysum[p * kBN] += (cur[0] + cur[1]) + (cur[2] + cur[3]);
         }
       }
     }
@@ -207,15 +252,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) sweep_kernel(const SweepParam
   __syncthreads();
   {
     double* dst = prm.partial + ((int64_t)blockIdx.x * prm.max_seg + (cur_jt - jt_first)) * P * kBN;
-    for (int i = threadIdx.x; i < P * kBN; i += kGemmThreads) dst[i] = colacc[i] + colacc[P * kBN + i];
+    for (int i = threadIdx.x; i < P * kBN; i += kNarrowThreads) dst[i] = colacc[i] + colacc[P * kBN + i];
   }
 }
 
 // k[p][j] = sum over the CTAs whose range covers column tile jt of their slot - 1   (wgcna.py:915)
 __global__ void sweep_reduce_kernel(const double* __restrict__ partial, int G, int max_seg, int P,
                                     int64_t RT, int64_t T, int64_t ncols, double* __restrict__ k) {
+  const int kBN = blockDim.x;  // tile columns of the sweep that wrote the slots
   const int64_t jt = blockIdx.x;
-  const int col = threadIdx.x;  // 128
+  const int col = threadIdx.x;
   const int p = blockIdx.y;
   const int64_t j = jt * kBN + col;
   if (j >= ncols) return;
@@ -241,70 +287,110 @@ __global__ void sweep_reduce_kernel(const double* __restrict__ partial, int G, i
 // result exactly symmetric -- checkAdjMat's 1e-12 test (wgcna.py:1135) passes with margin.
 // Small integer powers are evaluated by repeated squaring (<= 2 ulp from libm's pow).
 // -------------------------------------------------------------------------------------------
-constexpr int kAdjStages = 4;
+constexpr int kAdjStages = 3;   // narrow-engine ring slots of the adjacency (two CTAs per SM)
+constexpr int kCrossStages = 4;  // wide-engine ring slots of the cross-correlation
+constexpr int kAdjPitch = 33;    // odd: the transposed (mirror) reads of the parked tile stay 2-way at worst
 
-__device__ __forceinline__ double int_pow(double s, int e) {
-  double r = 1.0, b = s;
+// s ** e by binary exponentiation for four values at once (same multiplication order for every value, so
+// a symmetric pair of correlations gives bitwise equal adjacencies)
+__device__ __forceinline__ void int_pow4(double (&s)[4], int e) {
+  double r[4] = {1.0, 1.0, 1.0, 1.0};
 #pragma unroll 1
-  while (e) {
-    if (e & 1) r *= b;
-    b *= b;
+  while (true) {
+    if (e & 1) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) r[u] *= s[u];
+    }
     e >>= 1;
+    if (!e) break;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) s[u] *= s[u];
   }
-  return r;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) s[u] = r[u];
 }
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// tiles_n counts 128-wide column tiles; a CTA takes the left or right 64 columns of one tile.
+__global__ void __launch_bounds__(kNarrowThreads, 2)
 adjacency_kernel(const double* __restrict__ Z, const uint8_t* __restrict__ bad, int64_t n,
                  int64_t ldk, int net_type, double power, int ipower, int64_t row0, int64_t nrows,
                  int symmetric, int64_t tiles_n, double* __restrict__ A) {
+  constexpr int kBN = kNarrowBN, kParts = 128 / kBN;
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, tig = lane & 3;
+  const int wm = warp >> 1, wn = warp & 1;
+  const int64_t tile = blockIdx.x / kParts, part = blockIdx.x % kParts;
   int64_t ti, tj;
-  if (symmetric) {  // blockIdx.x enumerates the upper triangle row by row
-    int64_t t = blockIdx.x, T = tiles_n;
+  if (symmetric) {  // the upper triangle of 128 x 128 tiles, row by row
+    int64_t t = tile, T = tiles_n;
     ti = (int64_t)floor((2.0 * T + 1.0 - sqrt((2.0 * T + 1.0) * (2.0 * T + 1.0) - 8.0 * (double)t)) / 2.0);
     while (ti > 0 && ti * T - ti * (ti - 1) / 2 > t) --ti;
     while ((ti + 1) * T - (ti + 1) * ti / 2 <= t) ++ti;
     tj = ti + (t - (ti * T - ti * (ti - 1) / 2));
   } else {
-    ti = blockIdx.x / tiles_n;
-    tj = blockIdx.x % tiles_n;
+    ti = tile / tiles_n;
+    tj = tile % tiles_n;
   }
-  const int64_t i0 = row0 + ti * kBM, j0 = tj * kBN;
+  const int64_t i0 = row0 + ti * kBM, j0 = tj * 128 + part * kBN;
   const int64_t iend = row0 + nrows;
   const bool mirror = symmetric && ti != tj;
+  if (j0 >= n) return;  // block-uniform
 
-  AccF64 acc;
-  acc.clear();
-  gemm_f64_tile<kAdjStages>(acc, smem, Z, Z, ldk, ldk, i0, n, j0, n);
+  double* wt = smem + warp * 64 * kAdjPitch;
+  {
+    AccF64 acc;
+    acc.clear();
+    gemm_f64_tile<kAdjStages, 2>(acc, smem, Z, Z, ldk, ldk, i0, n, j0, n);
+    park_acc<kAdjPitch>(acc, wt, lane);
+  }
 
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  const int64_t wi0 = i0 + wm * 64, wj0 = j0 + wn * 32;
+  {  // rows of the sub-tile, lane <-> column: one 256-byte store per row
+    const int64_t gj = wj0 + lane;
+    const bool cok = gj < n;
+    const bool cbad = cok ? bad[gj] : false;
+    // NaN flags of the 64 rows as two ballots (a load per row would serialise 64 global latencies)
+    const unsigned rbad_lo = __ballot_sync(0xffffffffu, wi0 + lane < n && bad[wi0 + lane]);
+    const unsigned rbad_hi = __ballot_sync(0xffffffffu, wi0 + 32 + lane < n && bad[wi0 + 32 + lane]);
+#pragma unroll 1
+    for (int r0 = 0; r0 < 64; r0 += 4) {  // four rows in flight: independent multiply chains
+      if (wi0 + r0 >= iend) break;  // warp-uniform
+      double a[4];
 #pragma unroll
-  for (int mi = 0; mi < 4; ++mi) {
+      for (int u = 0; u < 4; ++u) {
+        double c = wt[(r0 + u) * kAdjPitch + lane];
+        c = fmin(1.0, fmax(-1.0, c));
+        a[u] = net_transform(c, net_type);
+      }
+      if (ipower > 0) {
+        int_pow4(a, ipower);
+      } else {
 #pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-      const int64_t gi = i0 + wm * 64 + mi * 16 + g + ch * 8;
-      if (gi >= iend) continue;
-      const bool rbad = bad[gi];
-      double* out = A + (gi - row0) * n;
+        for (int u = 0; u < 4; ++u) a[u] = pow(a[u], power);
+      }
 #pragma unroll
-      for (int ni = 0; ni < 4; ++ni) {
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + u;
+        const int64_t gi = wi0 + r;
+        const bool rbad = ((r < 32 ? rbad_lo : rbad_hi) >> (r & 31)) & 1u;
+        if (cbad || rbad) a[u] = qnan;
+        if (cok && gi < iend) A[(gi - row0) * n + gj] = a[u];
+        if (mirror) wt[r * kAdjPitch + lane] = a[u];
+      }
+    }
+  }
+  if (mirror) {  // the transposed block, lane <-> row of the sub-tile: again 256-byte row segments
+    __syncwarp();
+#pragma unroll 1
+    for (int c = 0; c < 32; ++c) {
+      const int64_t gj = wj0 + c;
+      if (gj >= n) break;  // warp-uniform
 #pragma unroll
-        for (int cb = 0; cb < 2; ++cb) {
-          const int64_t gj = j0 + wn * 32 + ni * 8 + 2 * tig + cb;
-          if (gj >= n) continue;
-          double c = acc.v[mi][ni][ch * 2 + cb];
-          c = fmin(1.0, fmax(-1.0, c));
-          double s = net_transform(c, net_type);
-          double a;
-          if (ipower > 0) a = int_pow(s, ipower);
-          else a = pow(s, power);
-          if (rbad || bad[gj]) a = qnan;
-          out[gj] = a;
-          if (mirror) A[gj * n + gi] = a;
-        }
+      for (int h = 0; h < 2; ++h) {
+        const int r = h * 32 + lane;
+        const int64_t gi = wi0 + r;
+        if (gi < n) A[gj * n + gi] = wt[r * kAdjPitch + c];
       }
     }
   }
@@ -325,7 +411,7 @@ cross_cor_kernel(const double* __restrict__ Zx, const uint8_t* __restrict__ badx
   const int64_t i0 = (int64_t)blockIdx.y * kBM, j0 = (int64_t)blockIdx.x * kBN;
   AccF64 acc;
   acc.clear();
-  gemm_f64_tile<kAdjStages>(acc, smem, Zx, Zy, ldk, ldk, i0, n, j0, M);
+  gemm_f64_tile<kCrossStages>(acc, smem, Zx, Zy, ldk, ldk, i0, n, j0, M);
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 #pragma unroll
   for (int mi = 0; mi < 4; ++mi)
@@ -356,7 +442,7 @@ extern "C" int b200w_dev_cross_correlation(const double* dZx, const uint8_t* d_b
   if (!dZx || !d_badx || !dZy || !d_bady || !dC || n < 1 || M < 1 || m < 1)
     return fail(B200W_E_INVALID, "cross_correlation: bad args");
   if (int e = ensure_device(device)) return e;
-  const size_t smem = gemm_smem_bytes(kAdjStages);
+  const size_t smem = gemm_smem_bytes(kCrossStages);
   B200W_CUDA(cudaFuncSetAttribute(cross_cor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t rt = (n + kBM - 1) / kBM, ct = (M + kBN - 1) / kBN;
   if (rt > 65535) return fail(B200W_E_UNSUPPORTED, "cross_correlation: too many row tiles");
@@ -392,17 +478,19 @@ extern "C" int b200w_dev_sweep(const double* dZ, const uint8_t* d_bad, int64_t m
   if (int e = ensure_device(device)) return e;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t ldk = b200w_padded_k(m);
+  constexpr int kBN = kNarrowBN;
   const int64_t CT = (ncols + kBN - 1) / kBN, RT = (n + kBM - 1) / kBM, T = CT * RT;
   int sms = 0;
   B200W_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-  const int G = (int)(T < sms ? T : sms);  // persistent: one CTA per SM, equal tile ranges
+  const int64_t resident = 2 * (int64_t)sms;
+  const int G = (int)(T < resident ? T : resident);  // persistent: two CTAs per SM, equal tile ranges
   const int max_seg = (int)((T / G + 1 + RT - 1) / RT + 1);
 
-  const size_t smem_max = gemm_smem_bytes(kSweepStages) + (size_t)2 * kSweepMaxP * kBN * 8;
+  const size_t smem_max = Narrow::smem_bytes(kSweepStages) + (size_t)2 * kSweepMaxP * kBN * 8;
   B200W_CUDA(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem_max));
   for (int p0 = 0; p0 < P; p0 += kSweepMaxP) {
-    // the chain restarts from 1 for each chunk of 32 powers, so the first step of a later chunk is
+    // the chain restarts from 1 for each chunk of 20 powers, so the first step of a later chunk is
     // the whole power reached so far (pow() with a large exponent: the value the reference's chain
     // approximates to ~1e-15).
     const int Pc = (P - p0 < kSweepMaxP) ? P - p0 : kSweepMaxP;
@@ -411,16 +499,19 @@ extern "C" int b200w_dev_sweep(const double* dZ, const uint8_t* d_bad, int64_t m
     prm.RT = RT; prm.T = T; prm.P = Pc; prm.net_type = net_type; prm.max_seg = max_seg;
     double base = 0.0;
     for (int q = 0; q < p0; ++q) base += h_steps[q];
+    prm.simple_steps = 1;
+    for (int q = 0; q < kSweepMaxP; ++q) { prm.step[q] = 1.0; prm.istep[q] = 1; }
     for (int q = 0; q < Pc; ++q) {
       double s = h_steps[p0 + q] + (q == 0 ? base : 0.0);
       prm.step[q] = s;
       prm.istep[q] = (s == (double)(int)s && s >= 1.0 && s <= 4.0) ? (int)s : 0;
+      if (prm.istep[q] != 1 && prm.istep[q] != 2) prm.simple_steps = 0;
     }
     Scratch part;
     B200W_CUDA(part.alloc((size_t)G * max_seg * Pc * kBN * sizeof(double), st));
     prm.partial = part.as<double>();
-    const size_t smem = gemm_smem_bytes(kSweepStages) + (size_t)2 * Pc * kBN * 8;
-    sweep_kernel<<<G, kGemmThreads, smem, st>>>(prm);
+    const size_t smem = Narrow::smem_bytes(kSweepStages) + (size_t)2 * Pc * kBN * 8;
+    sweep_kernel<<<G, kNarrowThreads, smem, st>>>(prm);
     B200W_LAUNCHED();
     dim3 rgrid((unsigned)CT, (unsigned)Pc);
     sweep_reduce_kernel<<<rgrid, kBN, 0, st>>>(prm.partial, G, max_seg, Pc, RT, T, ncols,
@@ -438,15 +529,15 @@ extern "C" int b200w_dev_adjacency(const double* dZ, const uint8_t* d_bad, int64
   if (net_type < 0 || net_type > 2) return fail(B200W_E_INVALID, "adjacency: bad network type");
   if (int e = ensure_device(device)) return e;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t smem = gemm_smem_bytes(kAdjStages);
+  const size_t smem = Narrow::smem_bytes(kAdjStages);
   B200W_CUDA(cudaFuncSetAttribute(adjacency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
   int ipower = (power == (double)(int)power && power >= 1.0 && power <= 64.0) ? (int)power : 0;
-  const int64_t row_tiles = (nrows + kBM - 1) / kBM, col_tiles = (n + kBN - 1) / kBN;
+  const int64_t row_tiles = (nrows + kBM - 1) / kBM, col_tiles = (n + 127) / 128;
   const int symmetric = (row0 == 0 && nrows == n) ? 1 : 0;
-  const int64_t blocks = symmetric ? col_tiles * (col_tiles + 1) / 2 : row_tiles * col_tiles;
+  const int64_t blocks = 2 * (symmetric ? col_tiles * (col_tiles + 1) / 2 : row_tiles * col_tiles);
   if (blocks > 2147483647LL) return fail(B200W_E_UNSUPPORTED, "adjacency: too many tiles");
-  adjacency_kernel<<<(unsigned)blocks, kGemmThreads, smem, st>>>(dZ, d_bad, n, b200w_padded_k(m),
+  adjacency_kernel<<<(unsigned)blocks, kNarrowThreads, smem, st>>>(dZ, d_bad, n, b200w_padded_k(m),
                                                                   net_type, power, ipower, row0, nrows,
                                                                   symmetric, col_tiles, dA);
   B200W_LAUNCHED();

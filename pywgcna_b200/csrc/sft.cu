@@ -12,6 +12,7 @@
 // One CTA per power; k[P, n] is 3.2 MB at C2, so this is a latency-sized kernel (~30 us), not a
 // bandwidth one -- it removes the 3.2 MB D2H + ~8 ms of host sorting from every step.
 #include "common.cuh"
+#include <climits>
 
 namespace b200w {
 
@@ -40,34 +41,67 @@ __device__ __forceinline__ T block_reduce(T v, T* red, Op op) {
   return r;
 }
 
-// rank-r order statistic (0-based) of row[0..n) by 11-bit radix select on the sortable keys
+// hist[bin] += 1 with the lanes of a warp that hit the same bin combined first: the top radix digit (sign +
+// exponent) and the exponent buckets put almost every element of a row into two or three bins
+__device__ __forceinline__ void hist_add(unsigned int* hist, unsigned int bin, bool active) {
+  const unsigned int live = __ballot_sync(0xffffffffu, active);
+  if (!active) return;
+  const unsigned int peers = __match_any_sync(live, bin);
+  if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], (unsigned int)__popc(peers));
+}
+
+// rank-r order statistic (0-based) of row[0..n) by 11-bit radix select on the sortable keys.  The bin that
+// holds the rank is found by a block-wide prefix sum over the 2048 counters (8 per thread).
 __device__ double radix_select(const double* __restrict__ row, int64_t n, int64_t r, unsigned int* hist) {
   unsigned long long prefix = 0, mask = 0;
-  __shared__ unsigned long long s_prefix;
+  __shared__ unsigned int s_warp_tot[kSftThreads / 32];
+  __shared__ unsigned int s_bin;
   __shared__ long long s_rank;
+  constexpr int kPer = 2048 / kSftThreads;  // counters per thread
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int shift = 53; shift >= -2; shift -= 11) {
     const int sh = shift < 0 ? 0 : shift;
     const int bits = shift < 0 ? 11 + shift : 11;  // last pass covers the remaining low bits
     const unsigned int nb = 1u << bits;
-    for (unsigned int i = threadIdx.x; i < nb; i += kSftThreads) hist[i] = 0;
+    for (unsigned int i = threadIdx.x; i < 2048; i += kSftThreads) hist[i] = 0;
     __syncthreads();
-    for (int64_t i = threadIdx.x; i < n; i += kSftThreads) {
-      const unsigned long long k = sortable_key(row[i]);
-      if ((k & mask) == prefix) atomicAdd(&hist[(unsigned int)((k >> sh) & (nb - 1))], 1u);
+    for (int64_t i0 = 0; i0 < n; i0 += kSftThreads) {  // whole warps stay in the loop for the ballots
+      const int64_t i = i0 + threadIdx.x;
+      unsigned long long k = 0;
+      bool hit = false;
+      if (i < n) {
+        k = sortable_key(row[i]);
+        hit = (k & mask) == prefix;
+      }
+      hist_add(hist, (unsigned int)((k >> sh) & (nb - 1)), hit);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      long long rr = r;
-      unsigned int b = 0;
-      for (; b < nb; ++b) {
-        if (rr < (long long)hist[b]) break;
-        rr -= hist[b];
+    // exclusive prefix over the counters: thread t owns bins [t * kPer, (t + 1) * kPer)
+    unsigned int mine[kPer], tot = 0;
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) { mine[q] = hist[threadIdx.x * kPer + q]; tot += mine[q]; }
+    unsigned int incl = tot;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp_tot[warp] = incl;
+    __syncthreads();
+    unsigned int before = incl - tot;
+    for (int w = 0; w < warp; ++w) before += s_warp_tot[w];
+    // exactly one thread has before <= r < before + tot
+    if ((long long)before <= r && r < (long long)before + (long long)tot) {
+      long long rr = r - before;
+      int q = 0;
+      for (; q < kPer - 1; ++q) {
+        if (rr < (long long)mine[q]) break;
+        rr -= mine[q];
       }
-      s_prefix = prefix | ((unsigned long long)b << sh);
+      s_bin = threadIdx.x * kPer + q;
       s_rank = rr;
     }
     __syncthreads();
-    prefix = s_prefix;
+    prefix |= (unsigned long long)s_bin << sh;
     r = s_rank;
     mask |= (unsigned long long)(nb - 1) << sh;
     __syncthreads();
@@ -77,10 +111,13 @@ __device__ double radix_select(const double* __restrict__ row, int64_t n, int64_
 
 // stats row layout: [0] min [1] max [2] median [3] plain float64 sum (informational) [4..4+nb) counts
 // [4+nb..4+2nb) bin sums
+// cached != 0: the row is first copied into dynamic shared memory and every pass reads it from there
 __global__ void __launch_bounds__(kSftThreads)
-sft_stats_kernel(const double* __restrict__ k, int64_t n, int64_t ldk, int nb, double* __restrict__ stats,
-                 long long* __restrict__ buckets) {
+sft_stats_kernel(const double* __restrict__ k, int64_t n, int64_t ldk, int nb, int cached,
+                 double* __restrict__ stats, long long* __restrict__ buckets) {
+  extern __shared__ __align__(16) double row_cache[];
   __shared__ double red_d[kSftThreads / 32];
+  __shared__ long long red_l[kSftThreads / 32];
   __shared__ unsigned int hist[2048];
   __shared__ long long bk_lo[kExpBuckets], bk_hi[kExpBuckets];
   __shared__ double edges[kSftMaxBreaks + 1];
@@ -91,9 +128,11 @@ sft_stats_kernel(const double* __restrict__ k, int64_t n, int64_t ldk, int nb, d
   double mn = INFINITY, mx = -INFINITY;
   for (int64_t i = threadIdx.x; i < n; i += kSftThreads) {
     const double v = row[i];
+    if (cached) row_cache[i] = v;
     mn = fmin(mn, v);
     mx = fmax(mx, v);
   }
+  if (cached) row = row_cache;  // (the reductions below start with a __syncthreads)
   mn = block_reduce(mn, red_d, [](double a, double b) { return fmin(a, b); });
   mx = block_reduce(mx, red_d, [](double a, double b) { return fmax(a, b); });
 
@@ -113,11 +152,15 @@ sft_stats_kernel(const double* __restrict__ k, int64_t n, int64_t ldk, int nb, d
   for (int i = threadIdx.x; i < kExpBuckets; i += kSftThreads) { bk_lo[i] = 0; bk_hi[i] = 0; }
   __syncthreads();
 
-  // histogram (bin = #edges < k, minus 1: right-closed bins) + exact mantissa sums per exponent
+  // histogram (bin = #edges < k, minus 1: right-closed bins) + exact mantissa sums per exponent.  A thread
+  // keeps the sums of its current exponent in registers and only touches the shared counters when the
+  // exponent changes (the connectivities of one power span two or three exponents).
   double cnt[kSftMaxBreaks], sum[kSftMaxBreaks];
 #pragma unroll
   for (int b = 0; b < kSftMaxBreaks; ++b) { cnt[b] = 0.0; sum[b] = 0.0; }
   double plain = 0.0;
+  int cur_ex = INT_MIN;
+  long long acc_lo = 0, acc_hi = 0;
   for (int64_t i = threadIdx.x; i < n; i += kSftThreads) {
     const double v = row[i];
     int bin = -1;
@@ -133,9 +176,22 @@ sft_stats_kernel(const double* __restrict__ k, int64_t n, int64_t ldk, int nb, d
       const double m = frexp(v, &ex);                       // v = m * 2^ex, 0.5 <= |m| < 1
       const long long M = (long long)(m * 9007199254740992.0);  // m * 2^53, exact
       const long long hi = M >> 27, lo = M - (hi << 27);
-      atomicAdd((unsigned long long*)&bk_lo[ex + kExpBias], (unsigned long long)lo);
-      atomicAdd((unsigned long long*)&bk_hi[ex + kExpBias], (unsigned long long)hi);
+      if (ex != cur_ex) {
+        if (cur_ex != INT_MIN) {
+          atomicAdd((unsigned long long*)&bk_lo[cur_ex + kExpBias], (unsigned long long)acc_lo);
+          atomicAdd((unsigned long long*)&bk_hi[cur_ex + kExpBias], (unsigned long long)acc_hi);
+        }
+        cur_ex = ex;
+        acc_lo = 0;
+        acc_hi = 0;
+      }
+      acc_lo += lo;  // |lo| < 2^27, |hi| < 2^26: no overflow below 2^36 elements per thread
+      acc_hi += hi;
     }
+  }
+  if (cur_ex != INT_MIN) {
+    atomicAdd((unsigned long long*)&bk_lo[cur_ex + kExpBias], (unsigned long long)acc_lo);
+    atomicAdd((unsigned long long*)&bk_hi[cur_ex + kExpBias], (unsigned long long)acc_hi);
   }
   auto add = [](double a, double b) { return a + b; };
   for (int b = 0; b < nb; ++b) {
@@ -153,11 +209,21 @@ sft_stats_kernel(const double* __restrict__ k, int64_t n, int64_t ldk, int nb, d
     buckets[((int64_t)p * kExpBuckets + i) * 2] = bk_lo[i];
     buckets[((int64_t)p * kExpBuckets + i) * 2 + 1] = bk_hi[i];
   }
-  // statistics.median: middle element, or the mean of the two middle elements
+  // statistics.median: middle element, or the mean of the two middle elements.  The lower middle element
+  // (rank n/2 - 1) is the upper one again when enough copies of it or smaller values sit below rank n/2,
+  // otherwise the largest value below it: one counting pass instead of a second select.
   const double m_hi = radix_select(row, n, n / 2, hist);
   double med = m_hi;
   if ((n & 1) == 0) {
-    const double m_lo = radix_select(row, n, n / 2 - 1, hist);
+    long long less = 0;
+    double below = -INFINITY;
+    for (int64_t i = threadIdx.x; i < n; i += kSftThreads) {
+      const double v = row[i];
+      if (v < m_hi) { ++less; below = fmax(below, v); }
+    }
+    less = block_reduce(less, red_l, [](long long a, long long b) { return a + b; });
+    below = block_reduce(below, red_d, [](double a, double b) { return fmax(a, b); });
+    const double m_lo = (n / 2 - 1 >= less) ? m_hi : below;
     med = (m_lo + m_hi) / 2.0;
   }
   if (threadIdx.x == 0) { out[0] = mn; out[1] = mx; out[2] = med; out[3] = plain; }
@@ -174,8 +240,14 @@ extern "C" int b200w_dev_sft_stats(const double* d_k, int P, int64_t n, int64_t 
   if (!d_k || !d_stats || !d_buckets || P < 1 || n < 1 || ldk < n || nbreaks < 1 || nbreaks > kSftMaxBreaks)
     return fail(B200W_E_INVALID, "sft_stats: bad args");
   if (int e = ensure_device(device)) return e;
-  sft_stats_kernel<<<P, kSftThreads, 0, (cudaStream_t)stream>>>(d_k, n, ldk, nbreaks, d_stats,
-                                                                  (long long*)d_buckets);
+  // rows up to ~22k connectivities are staged in shared memory (one global read instead of ten)
+  static const size_t kCacheMax = 176 * 1024;
+  const size_t row_bytes = (size_t)n * sizeof(double);
+  const int cached = row_bytes <= kCacheMax ? 1 : 0;
+  if (cached)
+    B200W_CUDA(cudaFuncSetAttribute(sft_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCacheMax));
+  sft_stats_kernel<<<P, kSftThreads, cached ? row_bytes : 0, (cudaStream_t)stream>>>(
+      d_k, n, ldk, nbreaks, cached, d_stats, (long long*)d_buckets);
   B200W_LAUNCHED();
   return 0;
 }
