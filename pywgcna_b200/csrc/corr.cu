@@ -125,6 +125,7 @@ struct SweepParams {
   int max_seg;          // partial slots per CTA
   int simple_steps;     // every istep is 1 or 2
   double* partial;      // [gridDim.x][max_seg][P][64]
+  double* sim;          // optional n x n output: the transformed similarity as adjacency() sees it (below)
   double step[kSweepMaxP];
   int istep[kSweepMaxP];
 };
@@ -187,7 +188,10 @@ __global__ void __launch_bounds__(kNarrowThreads, 2) sweep_kernel(const SweepPar
     const bool cbad = bad_col[col];
     double* mysum = colacc + (size_t)wm * P * kBN + col;  // [p * kBN]: this thread's own sums
 
-    // similarity and chain start of one element: wgcna.py:884-897, NaN skipped by nansum (:915)
+    // similarity and chain start of one element: wgcna.py:884-897, NaN skipped by nansum (:915).
+    // With prm.sim the similarity is also written out the way WGCNA.adjacency forms it before the power
+    // (wgcna.py:1097-1107: diagonal not forced, NaN rows and columns kept), so that the adjacency of the
+    // same data can be finished by an elementwise pass instead of a second correlation product.
     auto load = [&](int r, double& sv, double& c0) {
       const int row = wm * 64 + r;
       const int64_t gi = i0 + row;
@@ -195,8 +199,11 @@ __global__ void __launch_bounds__(kNarrowThreads, 2) sweep_kernel(const SweepPar
       c = fmin(1.0, fmax(-1.0, c));  // np.corrcoef clips to [-1, 1]
       sv = net_transform(c, prm.net_type);
       c0 = 1.0;
+      const bool nan_pair = cbad || bad_row[row];
+      if (prm.sim != nullptr && gi < n && gj < jend)
+        prm.sim[gi * n + gj] = nan_pair ? __longlong_as_double(0x7ff8000000000000LL) : sv;
       if (gi == gj) sv = 1.0;  // wgcna.py:897 (even for a NaN gene)
-      else if (cbad || bad_row[row]) { sv = 0.0; c0 = 0.0; }
+      else if (nan_pair) { sv = 0.0; c0 = 0.0; }
       if (gi >= n) { sv = 0.0; c0 = 0.0; }
     };
 
@@ -396,6 +403,45 @@ adjacency_kernel(const double* __restrict__ Z, const uint8_t* __restrict__ bad, 
   }
 }
 
+// Adjacency from a similarity matrix the sweep left behind (SweepParams::sim): A <- S ** power in place, the
+// same multiplication order as adjacency_kernel, so both routes give bitwise equal matrices.  HBM bound:
+// 16 bytes per element.
+__global__ void __launch_bounds__(256)
+similarity_power_kernel(double* __restrict__ A, int64_t total, double power, int ipower) {
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t e0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; e0 < total; e0 += stride) {
+    double a[4];
+    if (e0 + 4 <= total) {
+      const double2 lo = *reinterpret_cast<const double2*>(A + e0), hi = *reinterpret_cast<const double2*>(A + e0 + 2);
+      a[0] = lo.x; a[1] = lo.y; a[2] = hi.x; a[3] = hi.y;
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a[u] = (e0 + u < total) ? A[e0 + u] : 0.0;
+    }
+    bool nan[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) nan[u] = isnan(a[u]);
+    if (ipower > 0) {
+      int_pow4(a, ipower);
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a[u] = pow(a[u], power);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (nan[u]) a[u] = qnan;
+    if (e0 + 4 <= total) {
+      *reinterpret_cast<double2*>(A + e0) = make_double2(a[0], a[1]);
+      *reinterpret_cast<double2*>(A + e0 + 2) = make_double2(a[2], a[3]);
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (e0 + u < total) A[e0 + u] = a[u];
+    }
+  }
+}
+
 // -------------------------------------------------------------------------------------------
 // Cross-correlation of two standardised gene sets, C[i, j] = cor(x_i, y_j): the n x M block that
 // CalculateSignedKME takes out of np.corrcoef(datExpr.T, datME.T) (wgcna.py:3486-3489) without forming
@@ -468,9 +514,41 @@ extern "C" int b200w_dev_standardize(const double* dX, int64_t m, int64_t n, dou
   return 0;
 }
 
+static int sweep_impl(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t n, const double* h_steps, int P,
+                      int net_type, int64_t col0, int64_t ncols, double* d_k, double* d_sim, int device,
+                      void* stream);
+
 extern "C" int b200w_dev_sweep(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t n,
                                const double* h_steps, int P, int net_type, int64_t col0,
                                int64_t ncols, double* d_k, int device, void* stream) {
+  return sweep_impl(dZ, d_bad, m, n, h_steps, P, net_type, col0, ncols, d_k, nullptr, device, stream);
+}
+
+extern "C" int b200w_dev_sweep_similarity(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t n,
+                                          const double* h_steps, int P, int net_type, double* d_k,
+                                          double* d_sim, int device, void* stream) {
+  if (!d_sim) return fail(B200W_E_INVALID, "sweep_similarity: bad args");
+  return sweep_impl(dZ, d_bad, m, n, h_steps, P, net_type, 0, n, d_k, d_sim, device, stream);
+}
+
+extern "C" int b200w_dev_adjacency_from_similarity(double* d_sim_inout, int64_t n, double power, int device,
+                                                   void* stream) {
+  if (!d_sim_inout || n < 1 || !(power > 0.0)) return fail(B200W_E_INVALID, "adjacency_from_similarity: bad args");
+  if (int e = ensure_device(device)) return e;
+  int sms = 0;
+  B200W_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const int ipower = (power == (double)(int)power && power >= 1.0 && power <= 64.0) ? (int)power : 0;
+  const int64_t total = n * n, per_block = 256 * 4;
+  int64_t blocks = (total + per_block - 1) / per_block;
+  if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
+  similarity_power_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_sim_inout, total, power, ipower);
+  B200W_LAUNCHED();
+  return 0;
+}
+
+static int sweep_impl(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t n, const double* h_steps, int P,
+                      int net_type, int64_t col0, int64_t ncols, double* d_k, double* d_sim, int device,
+                      void* stream) {
   if (!dZ || !d_bad || !h_steps || !d_k || P < 1 || n < 1 || col0 < 0 || ncols < 1 ||
       col0 + ncols > n)
     return fail(B200W_E_INVALID, "sweep: bad args");
@@ -497,6 +575,7 @@ extern "C" int b200w_dev_sweep(const double* dZ, const uint8_t* d_bad, int64_t m
     SweepParams prm;
     prm.Z = dZ; prm.bad = d_bad; prm.n = n; prm.ldk = ldk; prm.col0 = col0; prm.ncols = ncols;
     prm.RT = RT; prm.T = T; prm.P = Pc; prm.net_type = net_type; prm.max_seg = max_seg;
+    prm.sim = (p0 == 0) ? d_sim : nullptr;  // one launch writes it
     double base = 0.0;
     for (int q = 0; q < p0; ++q) base += h_steps[q];
     prm.simple_steps = 1;

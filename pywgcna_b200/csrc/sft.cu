@@ -6,11 +6,13 @@
 //   histogram                      pd.cut(k, nBreaks) -> per-bin count and sum (:1018-1022), bins
 //                                  (e_i, e_i+1] with numpy's linspace arithmetic and the lowered first edge
 //   exact sum                      statistics.mean (:930) is the correctly rounded exact mean; every double
-//                                  is M * 2^e with a 53-bit integer M: the kernel adds the 27-bit halves of
-//                                  M into int64 counters per exponent (integer atomics: exact, order free),
-//                                  the host combines the ~50 non-empty counters as Python integers.
-// One CTA per power; k[P, n] is 3.2 MB at C2, so this is a latency-sized kernel (~30 us), not a
-// bandwidth one -- it removes the 3.2 MB D2H + ~8 ms of host sorting from every step.
+//                                  is M * 2^e with a 53-bit integer M: the kernel adds the five 11-bit pieces
+//                                  of M into int32 counters per exponent (integer atomics: exact, order free)
+//                                  and hands them over as (lo, hi) int64 pairs meaning lo + hi * 2^27; the
+//                                  host combines the ~50 non-empty pairs as Python integers.
+// One CTA per power; a row of k (160 KB at C2) is staged in shared memory once and read by all passes --
+// a latency-sized kernel, not a bandwidth one: it removes the 3.2 MB D2H + ~8 ms of host sorting from
+// every step.
 #include "common.cuh"
 #include <climits>
 
@@ -20,6 +22,7 @@ constexpr int kSftThreads = 256;
 constexpr int kSftMaxBreaks = 16;
 constexpr int kExpBuckets = 2304;  // frexp exponent + 1100 in [27, 2124]
 constexpr int kExpBias = 1100;
+constexpr int kPieces = 5;
 
 __device__ __forceinline__ unsigned long long sortable_key(double x) {
   unsigned long long u = (unsigned long long)__double_as_longlong(x);
@@ -115,11 +118,13 @@ __device__ double radix_select(const double* __restrict__ row, int64_t n, int64_
 __global__ void __launch_bounds__(kSftThreads)
 sft_stats_kernel(const double* __restrict__ k, int64_t n, int64_t ldk, int nb, int cached,
                  double* __restrict__ stats, long long* __restrict__ buckets) {
-  extern __shared__ __align__(16) double row_cache[];
+  extern __shared__ __align__(16) double dyn_smem[];
+  // dynamic shared memory: [kExpBuckets][kPieces] int sums of the mantissa pieces, then the optional row cache
+  int (*bk)[kPieces] = reinterpret_cast<int (*)[kPieces]>(dyn_smem);
+  double* row_cache = dyn_smem + kExpBuckets * kPieces * sizeof(int) / sizeof(double);
   __shared__ double red_d[kSftThreads / 32];
   __shared__ long long red_l[kSftThreads / 32];
   __shared__ unsigned int hist[2048];
-  __shared__ long long bk_lo[kExpBuckets], bk_hi[kExpBuckets];
   __shared__ double edges[kSftMaxBreaks + 1];
   const int p = blockIdx.x;
   const double* row = k + (int64_t)p * ldk;
@@ -149,18 +154,18 @@ sft_stats_kernel(const double* __restrict__ k, int64_t n, int64_t ldk, int nb, i
     edges[nb] = hi;
     if (mn != mx) edges[0] = __dsub_rn(edges[0], __dmul_rn(__dsub_rn(mx, mn), 0.001));
   }
-  for (int i = threadIdx.x; i < kExpBuckets; i += kSftThreads) { bk_lo[i] = 0; bk_hi[i] = 0; }
+  for (int i = threadIdx.x; i < kExpBuckets * kPieces; i += kSftThreads) (&bk[0][0])[i] = 0;
   __syncthreads();
 
-  // histogram (bin = #edges < k, minus 1: right-closed bins) + exact mantissa sums per exponent.  A thread
-  // keeps the sums of its current exponent in registers and only touches the shared counters when the
-  // exponent changes (the connectivities of one power span two or three exponents).
+  // histogram (bin = #edges < k, minus 1: right-closed bins) + exact mantissa sums per exponent: the 53-bit
+  // integer mantissa is cut into five 11-bit pieces that are added with native 32-bit shared-memory atomics
+  // (11 bits x n < 2^31 for n < 2^20 genes; b200w_dev_sft_stats rejects more).  64-bit shared atomics are
+  // compare-and-swap loops and took half of the kernel; warp-level pre-reduction by exponent
+  // (match.any + redux) measured slower than letting the atomic unit resolve the conflicts.
   double cnt[kSftMaxBreaks], sum[kSftMaxBreaks];
 #pragma unroll
   for (int b = 0; b < kSftMaxBreaks; ++b) { cnt[b] = 0.0; sum[b] = 0.0; }
   double plain = 0.0;
-  int cur_ex = INT_MIN;
-  long long acc_lo = 0, acc_hi = 0;
   for (int64_t i = threadIdx.x; i < n; i += kSftThreads) {
     const double v = row[i];
     int bin = -1;
@@ -173,25 +178,14 @@ sft_stats_kernel(const double* __restrict__ k, int64_t n, int64_t ldk, int nb, i
     plain += v;
     if (v != 0.0 && isfinite(v)) {
       int ex;
-      const double m = frexp(v, &ex);                       // v = m * 2^ex, 0.5 <= |m| < 1
-      const long long M = (long long)(m * 9007199254740992.0);  // m * 2^53, exact
-      const long long hi = M >> 27, lo = M - (hi << 27);
-      if (ex != cur_ex) {
-        if (cur_ex != INT_MIN) {
-          atomicAdd((unsigned long long*)&bk_lo[cur_ex + kExpBias], (unsigned long long)acc_lo);
-          atomicAdd((unsigned long long*)&bk_hi[cur_ex + kExpBias], (unsigned long long)acc_hi);
-        }
-        cur_ex = ex;
-        acc_lo = 0;
-        acc_hi = 0;
-      }
-      acc_lo += lo;  // |lo| < 2^27, |hi| < 2^26: no overflow below 2^36 elements per thread
-      acc_hi += hi;
+      const double m = frexp(v, &ex);                            // v = m * 2^ex, 0.5 <= |m| < 1
+      const long long M = (long long)(m * 9007199254740992.0);   // m * 2^53, exact
+      const long long mag = M < 0 ? -M : M;
+      const int sgn = M < 0 ? -1 : 1;
+#pragma unroll
+      for (int q = 0; q < kPieces; ++q)
+        atomicAdd(&bk[ex + kExpBias][q], sgn * (int)((mag >> (11 * q)) & 0x7ff));
     }
-  }
-  if (cur_ex != INT_MIN) {
-    atomicAdd((unsigned long long*)&bk_lo[cur_ex + kExpBias], (unsigned long long)acc_lo);
-    atomicAdd((unsigned long long*)&bk_hi[cur_ex + kExpBias], (unsigned long long)acc_hi);
   }
   auto add = [](double a, double b) { return a + b; };
   for (int b = 0; b < nb; ++b) {
@@ -206,8 +200,11 @@ sft_stats_kernel(const double* __restrict__ k, int64_t n, int64_t ldk, int nb, i
   plain = block_reduce(plain, red_d, add);
   __syncthreads();
   for (int i = threadIdx.x; i < kExpBuckets; i += kSftThreads) {
-    buckets[((int64_t)p * kExpBuckets + i) * 2] = bk_lo[i];
-    buckets[((int64_t)p * kExpBuckets + i) * 2 + 1] = bk_hi[i];
+    // the pair (lo, hi) the host reads stands for lo + hi * 2^27
+    const long long lo = (long long)bk[i][0] + (long long)bk[i][1] * (1LL << 11) + (long long)bk[i][2] * (1LL << 22);
+    const long long hi = (long long)bk[i][3] * (1LL << 6) + (long long)bk[i][4] * (1LL << 17);
+    buckets[((int64_t)p * kExpBuckets + i) * 2] = lo;
+    buckets[((int64_t)p * kExpBuckets + i) * 2 + 1] = hi;
   }
   // statistics.median: middle element, or the mean of the two middle elements.  The lower middle element
   // (rank n/2 - 1) is the upper one again when enough copies of it or smaller values sit below rank n/2,
@@ -240,13 +237,15 @@ extern "C" int b200w_dev_sft_stats(const double* d_k, int P, int64_t n, int64_t 
   if (!d_k || !d_stats || !d_buckets || P < 1 || n < 1 || ldk < n || nbreaks < 1 || nbreaks > kSftMaxBreaks)
     return fail(B200W_E_INVALID, "sft_stats: bad args");
   if (int e = ensure_device(device)) return e;
-  // rows up to ~22k connectivities are staged in shared memory (one global read instead of ten)
-  static const size_t kCacheMax = 176 * 1024;
+  if (n >= (1LL << 20)) return fail(B200W_E_UNSUPPORTED, "sft_stats: more than 2^20 - 1 genes");
+  // rows up to ~21k connectivities are staged in shared memory (one global read instead of ten)
+  static const size_t kCacheMax = 170 * 1024, kBucketBytes = (size_t)kExpBuckets * kPieces * sizeof(int);
+  static_assert(kBucketBytes % sizeof(double) == 0, "row cache alignment");
   const size_t row_bytes = (size_t)n * sizeof(double);
   const int cached = row_bytes <= kCacheMax ? 1 : 0;
-  if (cached)
-    B200W_CUDA(cudaFuncSetAttribute(sft_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCacheMax));
-  sft_stats_kernel<<<P, kSftThreads, cached ? row_bytes : 0, (cudaStream_t)stream>>>(
+  B200W_CUDA(cudaFuncSetAttribute(sft_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(kBucketBytes + kCacheMax)));
+  sft_stats_kernel<<<P, kSftThreads, kBucketBytes + (cached ? row_bytes : 0), (cudaStream_t)stream>>>(
       d_k, n, ldk, nbreaks, cached, d_stats, (long long*)d_buckets);
   B200W_LAUNCHED();
   return 0;

@@ -41,7 +41,8 @@ class DeviceNetwork:
     """Expression matrix resident in HBM; sweep / adjacency / TOM without leaving the device."""
 
     def __init__(self, X, device: int = 0, networkType: str = "unsigned", group=None, world: int | None = None,
-                 rank: int | None = None, precision: str = "auto", use_dist: bool | None = None):
+                 rank: int | None = None, precision: str = "auto", use_dist: bool | None = None,
+                 keep_similarity: bool | None = None):
         self.lib = L.load()
         self.device = int(device)
         torch.cuda.set_device(self.device)
@@ -79,6 +80,12 @@ class DeviceNetwork:
         self.fused = (self.world > 1 and self.elt == 1
                       and os.environ.get("B200WGCNA_DIST", "fused") != "rowblock")
         self.A = None
+        self._sim_in_A = False  # self.A holds the similarity the last sweep left (see sweep / adjacency)
+        # single GPU: sweep() leaves the similarity in the adjacency buffer (overwriting a block an earlier
+        # adjacency() returned) and the next adjacency() finishes it elementwise
+        if keep_similarity is None:
+            keep_similarity = os.environ.get("B200WGCNA_KEEP_SIMILARITY", "1") != "0"
+        self.keep_similarity = bool(keep_similarity) and self.world == 1
         self.T = None
         self._T_raw = None
         self._peer_ptrs = None
@@ -102,6 +109,7 @@ class DeviceNetwork:
         L.check(self.lib.b200w_dev_standardize(self.X.data_ptr(), self.m, self.n, self.Z.data_ptr(),
                                                self.bad.data_ptr(), self.device, self._stream()))
         self._standardized = True
+        self._sim_in_A = False
 
     def _all_gather_rows(self, full: torch.Tensor):
         """In-place all-gather of the ``per``-row blocks of ``full`` ([op_rows, ...], contiguous)."""
@@ -119,6 +127,17 @@ class DeviceNetwork:
         P = len(powers)
         col0, ncols = (0, self.n) if self.world == 1 else (self.row0, self.nrows)
         kloc = torch.empty((P, max(ncols, 1)), dtype=torch.float64, device=self.dev)
+        if self.keep_similarity:
+            # single GPU: the sweep also writes the transformed similarity into the adjacency buffer, and
+            # adjacency() of the same data finishes it with an elementwise S ** power instead of forming the
+            # correlation a second time as the reference does (wgcna.py:882 and :1097)
+            if self.A is None:
+                self.A = torch.empty((self.n, self.n), dtype=torch.float64, device=self.dev)
+            L.check(self.lib.b200w_dev_sweep_similarity(self.Z.data_ptr(), self.bad.data_ptr(), self.m, self.n,
+                                                        steps.ctypes.data, P, self.net, kloc.data_ptr(),
+                                                        self.A.data_ptr(), self.device, self._stream()))
+            self._sim_in_A = True
+            return kloc
         if ncols > 0:
             L.check(self.lib.b200w_dev_sweep(self.Z.data_ptr(), self.bad.data_ptr(), self.m, self.n,
                                              steps.ctypes.data, P, self.net, col0, ncols, kloc.data_ptr(),
@@ -165,6 +184,11 @@ class DeviceNetwork:
             self.standardize()
         if self.A is None:
             self.A = torch.empty((max(self.nrows, 1), self.n), dtype=torch.float64, device=self.dev)
+        if self._sim_in_A:
+            self._sim_in_A = False  # consumed: the buffer turns into the adjacency
+            L.check(self.lib.b200w_dev_adjacency_from_similarity(self.A.data_ptr(), self.n, float(power),
+                                                                 self.device, self._stream()))
+            return self.A[:self.nrows]
         if self.nrows > 0:
             L.check(self.lib.b200w_dev_adjacency(self.Z.data_ptr(), self.bad.data_ptr(), self.m, self.n, self.net,
                                                  float(power), self.row0, self.nrows, self.A.data_ptr(),
@@ -222,6 +246,9 @@ class DeviceNetwork:
         self._peer_ptrs = (C.c_void_p * self.world)(*[int(p) for p in ptrs])
 
     def tom_prepare(self, A_rows: torch.Tensor | None = None):
+        if A_rows is None and self._sim_in_A:
+            raise RuntimeError("DeviceNetwork: the adjacency buffer holds the similarity of the last sweep; "
+                               "call adjacency(power) first")
         A_rows = self.A[:self.nrows] if A_rows is None else A_rows
         op = self._operand()
         self._A_rows = A_rows

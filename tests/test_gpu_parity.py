@@ -343,6 +343,34 @@ def test_device_sft_statistics(gpu, n):
     assert int(power) == int(p_ref)
 
 
+@pytest.mark.parametrize("net", ["unsigned", "signed", "signed hybrid"])
+@pytest.mark.parametrize("n,power", [(257, 6), (1001, 2.5), (130, 1)])
+def test_adjacency_from_sweep_similarity(gpu, net, n, power):
+    """Single-GPU chaining: the sweep leaves the transformed similarity in the adjacency buffer and adjacency()
+    finishes it elementwise.  Bitwise the same matrix as the correlation-product route (NaN / constant genes,
+    ragged sizes, integer and pow() powers), the same connectivities, and the buffer cannot be mistaken for
+    an adjacency."""
+    from pywgcna_b200.device import DeviceNetwork
+
+    X = make_expression(40, n, F=5, seed=3 * n)
+    X[:, 3] = 2.0       # zero variance -> NaN row / column
+    X[7, n - 2] = np.nan  # a NaN sample -> NaN row / column
+    powers = [1, 2, 3, 5]
+    chained = DeviceNetwork(X, device=0, networkType=net, keep_similarity=True)
+    plain = DeviceNetwork(X, device=0, networkType=net, keep_similarity=False)
+    k1, k0 = chained.sweep(powers).cpu().numpy(), plain.sweep(powers).cpu().numpy()
+    assert np.array_equal(k1, k0)
+    with pytest.raises(RuntimeError):
+        chained.tom_prepare()
+    A1 = chained.adjacency(power).cpu().numpy()
+    A0 = plain.adjacency(power).cpu().numpy()
+    assert np.isnan(A0[3]).all() and np.isnan(A0[:, n - 2]).all()
+    assert np.array_equal(A1, A0, equal_nan=True)
+    assert maxabs(A0, O.adjacency(pd.DataFrame(X), adjacencyType=net, power=power)) < TOL_F64
+    # a second adjacency() without a sweep in between takes the product route again
+    assert np.array_equal(chained.adjacency(2).cpu().numpy(), plain.adjacency(2).cpu().numpy(), equal_nan=True)
+
+
 @pytest.mark.parametrize("n,m", [(3, 4), (5, 9), (17, 4), (127, 9), (129, 4), (255, 9), (257, 4)])
 def test_tiny_and_ragged_sizes(gpu, n, m):
     """Sizes below / straddling every tile (128-row DMMA tiles, 256 x 256 tcgen05 tiles, 128-byte K blocks)."""
