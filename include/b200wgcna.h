@@ -161,17 +161,18 @@ int b200w_dev_standardize(const double* dX, int64_t m, int64_t n, double* dZ, ui
 int b200w_dev_sweep(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t n,
                     const double* h_steps, int P, int net_type, int64_t col0, int64_t ncols,
                     double* d_k /* P x ncols */, int device, void* stream);
-/* The sweep over all genes (col0 = 0, ncols = n) that also leaves the transformed similarity behind:
- * d_sim (n x n) = |cor| / (1 + cor) / 2 / max(cor, 0) as WGCNA.adjacency forms it before `** power`
- * (PyWGCNA/wgcna.py:1097-1107; NaN rows and columns kept, diagonal not forced).  The reference computes
- * np.corrcoef twice, in pickSoftThreshold (:882) and again in adjacency (:1097); with this pair the second
- * product becomes b200w_dev_adjacency_from_similarity, an in-place elementwise pass (A = S ** power,
- * :1111) whose result is bitwise equal to b200w_dev_adjacency's. */
+/* The sweep that also leaves the transformed similarity behind: d_sim = rows [col0, col0 + ncols) of the
+ * symmetric n x n matrix |cor| / (1 + cor) / 2 / max(cor, 0) as WGCNA.adjacency forms it before `** power`
+ * (PyWGCNA/wgcna.py:1097-1107; NaN rows and columns kept, diagonal not forced), ncols x n row-major.
+ * The reference computes np.corrcoef twice, in pickSoftThreshold (:882) and again in adjacency (:1097);
+ * with this pair the second product becomes b200w_dev_adjacency_from_similarity, an in-place elementwise
+ * pass (A = S ** power, :1111) whose result is bitwise equal to b200w_dev_adjacency's for the same rows. */
 int b200w_dev_sweep_similarity(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t n,
-                               const double* h_steps, int P, int net_type, double* d_k /* P x n */,
-                               double* d_sim /* n x n */, int device, void* stream);
-int b200w_dev_adjacency_from_similarity(double* d_sim_inout /* n x n */, int64_t n, double power, int device,
-                                        void* stream);
+                               const double* h_steps, int P, int net_type, int64_t col0, int64_t ncols,
+                               double* d_k /* P x ncols */, double* d_sim /* ncols x n */, int device,
+                               void* stream);
+int b200w_dev_adjacency_from_similarity(double* d_sim_inout /* nrows x n */, int64_t nrows, int64_t n,
+                                        double power, int device, void* stream);
 /* statistics of k[P, ldk >= n] as described at b200w_soft_threshold_stats; d_stats P x (4 + 2 nb),
  * d_buckets P x b200w_sft_exp_buckets() x 2 */
 int b200w_dev_sft_stats(const double* d_k, int P, int64_t n, int64_t ldk, int nbreaks, double* d_stats,

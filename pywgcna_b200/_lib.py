@@ -59,8 +59,8 @@ SIGNATURES = {
     "b200w_padded_k": (_i64, [_i64]),
     "b200w_dev_standardize": (_int, [_dp, _i64, _i64, _dp, _dp, _int, _dp]),
     "b200w_dev_sweep": (_int, [_dp, _dp, _i64, _i64, _dp, _int, _int, _i64, _i64, _dp, _int, _dp]),
-    "b200w_dev_sweep_similarity": (_int, [_dp, _dp, _i64, _i64, _dp, _int, _int, _dp, _dp, _int, _dp]),
-    "b200w_dev_adjacency_from_similarity": (_int, [_dp, _i64, _dbl, _int, _dp]),
+    "b200w_dev_sweep_similarity": (_int, [_dp, _dp, _i64, _i64, _dp, _int, _int, _i64, _i64, _dp, _dp, _int, _dp]),
+    "b200w_dev_adjacency_from_similarity": (_int, [_dp, _i64, _i64, _dbl, _int, _dp]),
     "b200w_dev_adjacency": (_int, [_dp, _dp, _i64, _i64, _int, _dbl, _i64, _i64, _dp, _int, _dp]),
     "b200w_dev_check_adjacency": (_int, [_dp, _i64, _dp, _int, _dp]),
     "b200w_padded_n": (_i64, [_i64]),

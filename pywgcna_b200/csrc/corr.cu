@@ -108,7 +108,7 @@ __device__ __forceinline__ void park_acc(const AccF64& acc, double* wt, int lane
 // -------------------------------------------------------------------------------------------
 constexpr int kSweepStages = 3;
 constexpr int kSweepMaxP = 20;   // 3 ring slots + 2 x 20 x 64 sums: two CTAs fit one SM
-constexpr int kSweepPitch = 40;  // doubles; conflict-free 16-byte parking stores
+constexpr int kSweepPitch = 41;  // doubles; odd, so the transposed re-read of the parked tile is 2-way at worst
 #ifndef B200W_SWEEP_ROWS
 #define B200W_SWEEP_ROWS 8
 #endif
@@ -125,7 +125,9 @@ struct SweepParams {
   int max_seg;          // partial slots per CTA
   int simple_steps;     // every istep is 1 or 2
   double* partial;      // [gridDim.x][max_seg][P][64]
-  double* sim;          // optional n x n output: the transformed similarity as adjacency() sees it (below)
+  double* sim;          // optional output: the transformed similarity as adjacency() sees it (below) ...
+  int sim_transposed;   // ... 0: sim[i * n + j] (whole matrix), 1: sim[(j - col0) * n + i] (this column block
+                        //     as the row block of the symmetric matrix: what a rank of the sharded path keeps)
   double step[kSweepMaxP];
   int istep[kSweepMaxP];
 };
@@ -200,8 +202,11 @@ __global__ void __launch_bounds__(kNarrowThreads, 2) sweep_kernel(const SweepPar
       sv = net_transform(c, prm.net_type);
       c0 = 1.0;
       const bool nan_pair = cbad || bad_row[row];
-      if (prm.sim != nullptr && gi < n && gj < jend)
-        prm.sim[gi * n + gj] = nan_pair ? __longlong_as_double(0x7ff8000000000000LL) : sv;
+      if (prm.sim != nullptr) {
+        const double s_out = nan_pair ? __longlong_as_double(0x7ff8000000000000LL) : sv;
+        if (prm.sim_transposed) wt[r * kSweepPitch + lane] = s_out;  // stored by the transposed pass below
+        else if (gi < n && gj < jend) prm.sim[gi * n + gj] = s_out;
+      }
       if (gi == gj) sv = 1.0;  // wgcna.py:897 (even for a NaN gene)
       else if (nan_pair) { sv = 0.0; c0 = 0.0; }
       if (gi >= n) { sv = 0.0; c0 = 0.0; }
@@ -252,6 +257,20 @@ __global__ void __launch_bounds__(kNarrowThreads, 2) sweep_kernel(const SweepPar
 #pragma unroll
           for (int u = 0; u < 4; ++u) cur[u] *= step_pow(s1[u], st, ist);
           mysum[p * kBN] += (cur[0] + cur[1]) + (cur[2] + cur[3]);
+        }
+      }
+    }
+    if (prm.sim != nullptr && prm.sim_transposed) {  // lane <-> row of the sub-tile: 256-byte row segments
+      __syncwarp();
+#pragma unroll 1
+      for (int c = 0; c < 32; ++c) {
+        const int64_t gjc = j0 + wn * 32 + c;
+        if (gjc >= jend) break;  // warp-uniform
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int r = h * 32 + lane;
+          const int64_t gi = i0 + wm * 64 + r;
+          if (gi < n) prm.sim[(gjc - prm.col0) * n + gi] = wt[r * kSweepPitch + c];
         }
       }
     }
@@ -525,20 +544,21 @@ extern "C" int b200w_dev_sweep(const double* dZ, const uint8_t* d_bad, int64_t m
 }
 
 extern "C" int b200w_dev_sweep_similarity(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t n,
-                                          const double* h_steps, int P, int net_type, double* d_k,
-                                          double* d_sim, int device, void* stream) {
+                                          const double* h_steps, int P, int net_type, int64_t col0,
+                                          int64_t ncols, double* d_k, double* d_sim, int device, void* stream) {
   if (!d_sim) return fail(B200W_E_INVALID, "sweep_similarity: bad args");
-  return sweep_impl(dZ, d_bad, m, n, h_steps, P, net_type, 0, n, d_k, d_sim, device, stream);
+  return sweep_impl(dZ, d_bad, m, n, h_steps, P, net_type, col0, ncols, d_k, d_sim, device, stream);
 }
 
-extern "C" int b200w_dev_adjacency_from_similarity(double* d_sim_inout, int64_t n, double power, int device,
-                                                   void* stream) {
-  if (!d_sim_inout || n < 1 || !(power > 0.0)) return fail(B200W_E_INVALID, "adjacency_from_similarity: bad args");
+extern "C" int b200w_dev_adjacency_from_similarity(double* d_sim_inout, int64_t nrows, int64_t n, double power,
+                                                   int device, void* stream) {
+  if (!d_sim_inout || n < 1 || nrows < 1 || nrows > n || !(power > 0.0))
+    return fail(B200W_E_INVALID, "adjacency_from_similarity: bad args");
   if (int e = ensure_device(device)) return e;
   int sms = 0;
   B200W_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   const int ipower = (power == (double)(int)power && power >= 1.0 && power <= 64.0) ? (int)power : 0;
-  const int64_t total = n * n, per_block = 256 * 4;
+  const int64_t total = nrows * n, per_block = 256 * 4;
   int64_t blocks = (total + per_block - 1) / per_block;
   if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
   similarity_power_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_sim_inout, total, power, ipower);
@@ -576,6 +596,7 @@ static int sweep_impl(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t
     prm.Z = dZ; prm.bad = d_bad; prm.n = n; prm.ldk = ldk; prm.col0 = col0; prm.ncols = ncols;
     prm.RT = RT; prm.T = T; prm.P = Pc; prm.net_type = net_type; prm.max_seg = max_seg;
     prm.sim = (p0 == 0) ? d_sim : nullptr;  // one launch writes it
+    prm.sim_transposed = (col0 == 0 && ncols == n) ? 0 : 1;
     double base = 0.0;
     for (int q = 0; q < p0; ++q) base += h_steps[q];
     prm.simple_steps = 1;

@@ -81,11 +81,11 @@ class DeviceNetwork:
                       and os.environ.get("B200WGCNA_DIST", "fused") != "rowblock")
         self.A = None
         self._sim_in_A = False  # self.A holds the similarity the last sweep left (see sweep / adjacency)
-        # single GPU: sweep() leaves the similarity in the adjacency buffer (overwriting a block an earlier
-        # adjacency() returned) and the next adjacency() finishes it elementwise
+        # sweep() leaves this rank's rows of the similarity in the adjacency buffer (overwriting a block an
+        # earlier adjacency() returned) and the next adjacency() finishes them elementwise
         if keep_similarity is None:
             keep_similarity = os.environ.get("B200WGCNA_KEEP_SIMILARITY", "1") != "0"
-        self.keep_similarity = bool(keep_similarity) and self.world == 1
+        self.keep_similarity = bool(keep_similarity)
         self.T = None
         self._T_raw = None
         self._peer_ptrs = None
@@ -127,18 +127,18 @@ class DeviceNetwork:
         P = len(powers)
         col0, ncols = (0, self.n) if self.world == 1 else (self.row0, self.nrows)
         kloc = torch.empty((P, max(ncols, 1)), dtype=torch.float64, device=self.dev)
-        if self.keep_similarity:
-            # single GPU: the sweep also writes the transformed similarity into the adjacency buffer, and
-            # adjacency() of the same data finishes it with an elementwise S ** power instead of forming the
-            # correlation a second time as the reference does (wgcna.py:882 and :1097)
+        if ncols > 0 and self.keep_similarity:
+            # the sweep also writes this rank's rows of the transformed similarity into the adjacency buffer,
+            # and adjacency() of the same data finishes them with an elementwise S ** power instead of forming
+            # the correlation a second time as the reference does (wgcna.py:882 and :1097)
             if self.A is None:
-                self.A = torch.empty((self.n, self.n), dtype=torch.float64, device=self.dev)
+                self.A = torch.empty((max(self.nrows, 1), self.n), dtype=torch.float64, device=self.dev)
             L.check(self.lib.b200w_dev_sweep_similarity(self.Z.data_ptr(), self.bad.data_ptr(), self.m, self.n,
-                                                        steps.ctypes.data, P, self.net, kloc.data_ptr(),
-                                                        self.A.data_ptr(), self.device, self._stream()))
+                                                        steps.ctypes.data, P, self.net, col0, ncols,
+                                                        kloc.data_ptr(), self.A.data_ptr(), self.device,
+                                                        self._stream()))
             self._sim_in_A = True
-            return kloc
-        if ncols > 0:
+        elif ncols > 0:
             L.check(self.lib.b200w_dev_sweep(self.Z.data_ptr(), self.bad.data_ptr(), self.m, self.n,
                                              steps.ctypes.data, P, self.net, col0, ncols, kloc.data_ptr(),
                                              self.device, self._stream()))
@@ -186,8 +186,8 @@ class DeviceNetwork:
             self.A = torch.empty((max(self.nrows, 1), self.n), dtype=torch.float64, device=self.dev)
         if self._sim_in_A:
             self._sim_in_A = False  # consumed: the buffer turns into the adjacency
-            L.check(self.lib.b200w_dev_adjacency_from_similarity(self.A.data_ptr(), self.n, float(power),
-                                                                 self.device, self._stream()))
+            L.check(self.lib.b200w_dev_adjacency_from_similarity(self.A.data_ptr(), self.nrows, self.n,
+                                                                 float(power), self.device, self._stream()))
             return self.A[:self.nrows]
         if self.nrows > 0:
             L.check(self.lib.b200w_dev_adjacency(self.Z.data_ptr(), self.bad.data_ptr(), self.m, self.n, self.net,

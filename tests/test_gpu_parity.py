@@ -369,6 +369,14 @@ def test_adjacency_from_sweep_similarity(gpu, net, n, power):
     assert maxabs(A0, O.adjacency(pd.DataFrame(X), adjacencyType=net, power=power)) < TOL_F64
     # a second adjacency() without a sweep in between takes the product route again
     assert np.array_equal(chained.adjacency(2).cpu().numpy(), plain.adjacency(2).cpu().numpy(), equal_nan=True)
+    # sharded path: a rank's column-block sweep leaves its row block (transposed store)
+    for rank in range(2):
+        part = DeviceNetwork(X, device=0, networkType=net, world=2, rank=rank, use_dist=False, keep_similarity=True)
+        kT = part.sweep(powers).cpu().numpy()
+        rows = slice(part.row0, part.row0 + part.nrows)
+        assert np.array_equal(kT[:, rows], k0[:, rows])
+        if part.nrows:
+            assert np.array_equal(part.adjacency(power).cpu().numpy(), A0[rows], equal_nan=True)
 
 
 @pytest.mark.parametrize("n,m", [(3, 4), (5, 9), (17, 4), (127, 9), (129, 4), (255, 9), (257, 4)])
