@@ -105,6 +105,13 @@ __device__ __forceinline__ void park_acc(const AccF64& acc, double* wt, int lane
 // (warp row, power, column); whenever the range crosses into the next column tile the sums are flushed to
 // a partial slot, and sweep_reduce_kernel adds the slots of a column tile in CTA order: deterministic,
 // no atomics.
+// Symmetric mode (whole matrix, steps 1 / 2): the similarity is symmetric, so only the tiles on and above the
+// diagonal are formed -- half the MMAs.  A tile strictly above the diagonal serves two sets of genes: its
+// column sums go to the genes of its columns as before, and a second epilogue pass over the parked tile with
+// lane <-> row gives the row sums for the genes of its rows (their column tiles never visit these rows);
+// those go to a per-tile slot and sweep_reduce_sym_kernel adds, per gene, the column slots and the row
+// slots in a fixed order.  The chain is evaluated twice on such a tile, so the FP64 epilogue work per
+// matrix element stays what it was; the saving is the MMA half of the shared pipe.
 // -------------------------------------------------------------------------------------------
 constexpr int kSweepStages = 3;
 constexpr int kSweepMaxP = 20;   // 3 ring slots + 2 x 20 x 64 sums: two CTAs fit one SM
@@ -128,13 +135,28 @@ struct SweepParams {
   double* sim;          // optional output: the transformed similarity as adjacency() sees it (below) ...
   int sim_transposed;   // ... 0: sim[i * n + j] (whole matrix), 1: sim[(j - col0) * n + i] (this column block
                         //     as the row block of the symmetric matrix: what a rank of the sharded path keeps)
+  int symmetric;        // whole matrix, only tiles on and above the diagonal (see sweep_kernel)
+  double* rowpart;      // symmetric: [tile][P][128] row sums of the tiles above the diagonal
   double step[kSweepMaxP];
   int istep[kSweepMaxP];
 };
 
-__device__ __forceinline__ void sweep_range(int64_t T, int64_t G, int64_t b, int64_t& t0, int64_t& t1) {
+__host__ __device__ __forceinline__ void sweep_range(int64_t T, int64_t G, int64_t b, int64_t& t0, int64_t& t1) {
   t0 = T * b / G;
   t1 = T * (b + 1) / G;
+}
+
+// Symmetric sweep: column tile jt (64 wide, inside the 128-block jt / 2) only takes the row tiles 0 .. jt / 2,
+// enumerated column-major like the full grid.  sym_offset(jt) = number of tiles before column tile jt.
+__host__ __device__ __forceinline__ int64_t sym_offset(int64_t jt) {
+  const int64_t q = jt >> 1, r = jt & 1;
+  return (q + 1) * (q + r);
+}
+__host__ __device__ __forceinline__ int64_t sym_col_of(int64_t t) {  // largest jt with sym_offset(jt) <= t
+  int64_t jt = 2 * (int64_t)sqrt((double)t);
+  while (jt > 0 && sym_offset(jt) > t) --jt;
+  while (sym_offset(jt + 1) <= t) ++jt;
+  return jt;
 }
 
 __global__ void __launch_bounds__(kNarrowThreads, 2) sweep_kernel(const SweepParams prm) {
@@ -152,12 +174,21 @@ __global__ void __launch_bounds__(kNarrowThreads, 2) sweep_kernel(const SweepPar
   int64_t t0, t1;
   sweep_range(prm.T, gridDim.x, blockIdx.x, t0, t1);
   if (t0 >= t1) return;
-  const int64_t jt_first = t0 / prm.RT;
+  int64_t jt, it;
+  if (prm.symmetric) {
+    jt = sym_col_of(t0);
+    it = t0 - sym_offset(jt);
+  } else {
+    jt = t0 / prm.RT;
+    it = t0 - jt * prm.RT;
+  }
+  const int64_t jt_first = jt;
   int64_t cur_jt = -1;
 
-  for (int64_t t = t0; t < t1; ++t) {
-    const int64_t jt = t / prm.RT, it = t - jt * prm.RT;
+  for (int64_t t = t0; t < t1; ++t, ++it) {
+    if (it >= (prm.symmetric ? (jt >> 1) + 1 : prm.RT)) { ++jt; it = 0; }
     const int64_t j0 = prm.col0 + jt * kBN, i0 = it * kBM;
+    const bool two_pass = prm.symmetric && it < (jt >> 1);  // strictly above the diagonal block
     __syncthreads();  // every warp is done with the parked tile, bad_row and (on a flush) the sums
     if (jt != cur_jt) {  // entering a new column tile: flush the previous one, reset the sums
       if (cur_jt >= 0) {
@@ -260,6 +291,61 @@ __global__ void __launch_bounds__(kNarrowThreads, 2) sweep_kernel(const SweepPar
         }
       }
     }
+    if (two_pass) {
+      // rows lane and lane + 32 of the warp's 64, its 32 columns four at a time: row sums for the genes of
+      // the tile's rows, and the mirrored half of the similarity
+      double kr[2][kSweepMaxP];
+#pragma unroll
+      for (int p = 0; p < kSweepMaxP; ++p) kr[0][p] = kr[1][p] = 0.0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 32; c0 += 4) {
+        double s1[8], s2[8], cur[8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int r = h * 32 + lane, row = wm * 64 + r, colx = wn * 32 + c0 + u;
+            const int64_t gi = i0 + row, gjx = j0 + colx;
+            double c = wt[r * kSweepPitch + c0 + u];
+            c = fmin(1.0, fmax(-1.0, c));
+            double sv = net_transform(c, prm.net_type), c0v = 1.0;
+            const bool nan_pair = bad_col[colx] || bad_row[row];
+            const bool inside = gi < n && gjx < jend;
+            if (prm.sim != nullptr && inside)
+              prm.sim[gjx * n + gi] = nan_pair ? __longlong_as_double(0x7ff8000000000000LL) : sv;
+            if (nan_pair || !inside) { sv = 0.0; c0v = 0.0; }
+            s1[h * 4 + u] = sv;
+            s2[h * 4 + u] = sv * sv;
+            cur[h * 4 + u] = c0v;
+          }
+#pragma unroll
+        for (int p = 0; p < kSweepMaxP; ++p) {
+          if (p < P) {
+            const bool one = prm.istep[p] == 1;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) cur[e] *= one ? s1[e] : s2[e];
+            kr[0][p] += (cur[0] + cur[1]) + (cur[2] + cur[3]);
+            kr[1][p] += (cur[4] + cur[5]) + (cur[6] + cur[7]);
+          }
+        }
+      }
+      // the two warps that share rows add up through their own (now free) parking space
+      __syncwarp();
+#pragma unroll
+      for (int p = 0; p < kSweepMaxP; ++p)
+        if (p < P) {
+          wt[p * 64 + lane] = kr[0][p];
+          wt[p * 64 + 32 + lane] = kr[1][p];
+        }
+      __syncthreads();
+      {
+        const int row = threadIdx.x, rl = row & 63;
+        const double* w0 = smem + ((row >> 6) * 2) * 64 * kSweepPitch;
+        const double* w1 = w0 + 64 * kSweepPitch;
+        double* dst = prm.rowpart + t * P * kBM;
+        for (int p = 0; p < P; ++p) dst[p * kBM + row] = w0[p * 64 + rl] + w1[p * 64 + rl];
+      }
+    }
     if (prm.sim != nullptr && prm.sim_transposed) {  // lane <-> row of the sub-tile: 256-byte row segments
       __syncwarp();
 #pragma unroll 1
@@ -302,6 +388,33 @@ __global__ void sweep_reduce_kernel(const double* __restrict__ partial, int G, i
     s += partial[(((int64_t)b * max_seg + seg) * P + p) * kBN + col];
   }
   k[(int64_t)p * ncols + j] = s - 1.0;
+}
+
+// symmetric mode: k[p][j] = column slots of column tile jt (as above) + row slots of the tiles to the right of
+// gene j's 128-block, in column-tile order, - 1
+__global__ void sweep_reduce_sym_kernel(const double* __restrict__ partial, const double* __restrict__ rowpart,
+                                        int G, int max_seg, int P, int64_t CT, int64_t T, int64_t n,
+                                        double* __restrict__ k) {
+  constexpr int kBN = kNarrowBN;
+  const int64_t jt = blockIdx.x;
+  const int col = threadIdx.x;
+  const int p = blockIdx.y;
+  const int64_t j = jt * kBN + col;
+  if (j >= n) return;
+  const int64_t lo = sym_offset(jt), hi = sym_offset(jt + 1);
+  double s = 0.0;
+  for (int64_t b = lo * G / T; b < G; ++b) {
+    int64_t t0, t1;
+    sweep_range(T, G, b, t0, t1);
+    if (t0 >= hi) break;
+    if (t1 <= lo || t0 >= t1) continue;
+    const int64_t seg = jt - sym_col_of(t0);
+    s += partial[(((int64_t)b * max_seg + seg) * P + p) * kBN + col];
+  }
+  const int64_t I = j / kBM, local = j % kBM;
+  for (int64_t jt2 = 2 * I + 2; jt2 < CT; ++jt2)
+    s += rowpart[((sym_offset(jt2) + I) * P + p) * kBM + local];
+  k[(int64_t)p * n + j] = s - 1.0;
 }
 
 // -------------------------------------------------------------------------------------------
@@ -577,12 +690,14 @@ static int sweep_impl(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t ldk = b200w_padded_k(m);
   constexpr int kBN = kNarrowBN;
-  const int64_t CT = (ncols + kBN - 1) / kBN, RT = (n + kBM - 1) / kBM, T = CT * RT;
+  const int64_t CT = (ncols + kBN - 1) / kBN, RT = (n + kBM - 1) / kBM;
   int sms = 0;
   B200W_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   const int64_t resident = 2 * (int64_t)sms;
-  const int G = (int)(T < resident ? T : resident);  // persistent: two CTAs per SM, equal tile ranges
-  const int max_seg = (int)((T / G + 1 + RT - 1) / RT + 1);
+  static const bool sym_allowed = [] {
+    const char* e = getenv("B200W_SWEEP_SYMMETRIC");
+    return !(e && e[0] == '0');
+  }();
 
   const size_t smem_max = Narrow::smem_bytes(kSweepStages) + (size_t)2 * kSweepMaxP * kBN * 8;
   B200W_CUDA(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -594,7 +709,7 @@ static int sweep_impl(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t
     const int Pc = (P - p0 < kSweepMaxP) ? P - p0 : kSweepMaxP;
     SweepParams prm;
     prm.Z = dZ; prm.bad = d_bad; prm.n = n; prm.ldk = ldk; prm.col0 = col0; prm.ncols = ncols;
-    prm.RT = RT; prm.T = T; prm.P = Pc; prm.net_type = net_type; prm.max_seg = max_seg;
+    prm.RT = RT; prm.P = Pc; prm.net_type = net_type;
     prm.sim = (p0 == 0) ? d_sim : nullptr;  // one launch writes it
     prm.sim_transposed = (col0 == 0 && ncols == n) ? 0 : 1;
     double base = 0.0;
@@ -607,15 +722,37 @@ static int sweep_impl(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t
       prm.istep[q] = (s == (double)(int)s && s >= 1.0 && s <= 4.0) ? (int)s : 0;
       if (prm.istep[q] != 1 && prm.istep[q] != 2) prm.simple_steps = 0;
     }
-    Scratch part;
+    // whole matrix and a plain chain: only the tiles on and above the diagonal
+    const bool symmetric = sym_allowed && col0 == 0 && ncols == n && prm.simple_steps;
+    const int64_t T = symmetric ? sym_offset(CT) : CT * RT;
+    const int G = (int)(T < resident ? T : resident);  // persistent: two CTAs per SM, equal tile ranges
+    int max_seg = 1;  // column tiles one CTA range can touch
+    for (int b = 0; b < G; ++b) {
+      int64_t t0, t1;
+      sweep_range(T, G, b, t0, t1);
+      if (t0 >= t1) continue;
+      const int64_t first = symmetric ? sym_col_of(t0) : t0 / RT, last = symmetric ? sym_col_of(t1 - 1) : (t1 - 1) / RT;
+      if (last - first + 1 > max_seg) max_seg = (int)(last - first + 1);
+    }
+    prm.T = T; prm.max_seg = max_seg; prm.symmetric = symmetric ? 1 : 0;
+    Scratch part, rowpart;
     B200W_CUDA(part.alloc((size_t)G * max_seg * Pc * kBN * sizeof(double), st));
     prm.partial = part.as<double>();
+    prm.rowpart = nullptr;
+    if (symmetric) {
+      B200W_CUDA(rowpart.alloc((size_t)T * Pc * kBM * sizeof(double), st));
+      prm.rowpart = rowpart.as<double>();
+    }
     const size_t smem = Narrow::smem_bytes(kSweepStages) + (size_t)2 * Pc * kBN * 8;
     sweep_kernel<<<G, kNarrowThreads, smem, st>>>(prm);
     B200W_LAUNCHED();
     dim3 rgrid((unsigned)CT, (unsigned)Pc);
-    sweep_reduce_kernel<<<rgrid, kBN, 0, st>>>(prm.partial, G, max_seg, Pc, RT, T, ncols,
-                                               d_k + (int64_t)p0 * ncols);
+    if (symmetric)
+      sweep_reduce_sym_kernel<<<rgrid, kBN, 0, st>>>(prm.partial, prm.rowpart, G, max_seg, Pc, CT, T, n,
+                                                     d_k + (int64_t)p0 * ncols);
+    else
+      sweep_reduce_kernel<<<rgrid, kBN, 0, st>>>(prm.partial, G, max_seg, Pc, RT, T, ncols,
+                                                 d_k + (int64_t)p0 * ncols);
     B200W_LAUNCHED();
   }
   return 0;

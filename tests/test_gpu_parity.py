@@ -374,7 +374,8 @@ def test_adjacency_from_sweep_similarity(gpu, net, n, power):
         part = DeviceNetwork(X, device=0, networkType=net, world=2, rank=rank, use_dist=False, keep_similarity=True)
         kT = part.sweep(powers).cpu().numpy()
         rows = slice(part.row0, part.row0 + part.nrows)
-        assert np.array_equal(kT[:, rows], k0[:, rows])
+        # (the whole-matrix sweep takes the symmetric tile schedule: same sums in another order)
+        np.testing.assert_allclose(kT[:, rows], k0[:, rows], rtol=1e-12, atol=1e-12)
         if part.nrows:
             assert np.array_equal(part.adjacency(power).cpu().numpy(), A0[rows], equal_nan=True)
 
