@@ -5,7 +5,9 @@
 #include <string.h>
 #include <sys/mman.h>
 
+#include <chrono>
 #include <map>
+#include <string>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -168,6 +170,33 @@ struct Stream {
 // (2) a pool of page-locked buffers for the n x n RESULTS (b200w_host_alloc / b200w_host_free): first-touch
 //     page faults of a fresh 3.2 GB numpy array cost ~0.5 s and cudaHostAlloc 1.75 s, a recycled pinned
 //     buffer costs nothing and is written by DMA at 52 GB/s.
+// B200W_TRACE=1: per-phase wall times of the host entry points on stderr (every mark synchronises the
+// stream, so the phases are serialised while tracing)
+struct Trace {
+  const char* name;
+  cudaStream_t s;
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  std::string line;
+  Trace(const char* name_, cudaStream_t s_) : name(name_), s(s_) {
+    static const bool enabled = getenv("B200W_TRACE") != nullptr;
+    on = enabled;
+    if (on) t0 = std::chrono::steady_clock::now();
+  }
+  void mark(const char* what) {
+    if (!on) return;
+    if (s) cudaStreamSynchronize(s);
+    const auto t1 = std::chrono::steady_clock::now();
+    char buf[96];
+    snprintf(buf, sizeof buf, "  %s %.2f ms", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    line += buf;
+    t0 = t1;
+  }
+  ~Trace() {
+    if (on) fprintf(stderr, "[b200w] %s:%s\n", name, line.c_str());
+  }
+};
+
 struct HostPin {
   void* p = nullptr;
   void pin(const void* ptr, size_t bytes) {
@@ -389,23 +418,29 @@ extern "C" int b200w_adjacency(const double* X, int64_t m, int64_t n, int net_ty
   if (int e = ensure_device(device)) return e;
   Stream st;
   B200W_CUDA(st.create());
+  Trace tr("b200w_adjacency", st.s);
   DevBuf dX, dZ, dBad, dA;
   HostPin pin_out;
   pin_out.pin(A_out, (size_t)nrows * n * 8);
+  tr.mark("pin");
   const int64_t ldk = b200w_padded_k(m);
   B200W_CUDA(dX.alloc((size_t)m * n * 8));
   B200W_CUDA(dZ.alloc((size_t)n * ldk * 8));
   B200W_CUDA(dBad.alloc((size_t)n));
   B200W_CUDA(dA.alloc((size_t)nrows * n * 8));
+  tr.mark("alloc");
   B200W_CUDA(cudaMemcpyAsync(dX.p, X, (size_t)m * n * 8, cudaMemcpyHostToDevice, st.s));
+  tr.mark("h2d");
   if (int e = b200w_dev_standardize(dX.as<double>(), m, n, dZ.as<double>(), dBad.as<uint8_t>(),
                                     device, st.s))
     return e;
   if (int e = b200w_dev_adjacency(dZ.as<double>(), dBad.as<uint8_t>(), m, n, net_type, power, row0,
                                   nrows, dA.as<double>(), device, st.s))
     return e;
+  tr.mark("kernels");
   B200W_CUDA(cudaMemcpyAsync(A_out, dA.p, (size_t)nrows * n * 8, cudaMemcpyDeviceToHost, st.s));
   B200W_CUDA(cudaStreamSynchronize(st.s));
+  tr.mark("d2h");
   return 0;
 }
 
@@ -493,13 +528,17 @@ extern "C" int b200w_tom(const double* A, int64_t n, int tom_type, int tom_denom
   if (int e = ensure_device(device)) return e;
   Stream st;
   B200W_CUDA(st.create());
+  Trace tr("b200w_tom", st.s);
   DevBuf dA;
   HostPin pin_in, pin_out;
   pin_in.pin(A, (size_t)n * n * 8);
   pin_out.pin(out, (out_mode == B200W_OUT_DISS_COND || out_mode == B200W_OUT_DISS_R8_COND)
                        ? (size_t)n * (n - 1) / 2 * 8 : (size_t)nrows * n * 8);
+  tr.mark("pin");
   B200W_CUDA(dA.alloc((size_t)n * n * 8));
+  tr.mark("alloc");
   B200W_CUDA(cudaMemcpyAsync(dA.p, A, (size_t)n * n * 8, cudaMemcpyHostToDevice, st.s));
+  tr.mark("h2d");
   if (check) {
     DevBuf dS;
     double hs[4];
@@ -514,8 +553,11 @@ extern "C" int b200w_tom(const double* A, int64_t n, int tom_type, int tom_denom
       if (hs[1] < lo || hs[2] > 1.0) return B200W_CHECK_RANGE;
     }
   }
-  return tom_from_device_adjacency(dA.as<double>(), n, tom_type, tom_denom, out_mode, precision,
-                                   row0, nrows, out, device, st.s);
+  tr.mark("check");
+  const int rc = tom_from_device_adjacency(dA.as<double>(), n, tom_type, tom_denom, out_mode, precision,
+                                           row0, nrows, out, device, st.s);
+  tr.mark("prepare+contraction+d2h");
+  return rc;
 }
 
 extern "C" int b200w_network(const double* X, int64_t m, int64_t n, int net_type, double power,

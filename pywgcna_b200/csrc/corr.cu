@@ -723,7 +723,12 @@ static int sweep_impl(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t
       if (prm.istep[q] != 1 && prm.istep[q] != 2) prm.simple_steps = 0;
     }
     // whole matrix and a plain chain: only the tiles on and above the diagonal
-    const bool symmetric = sym_allowed && col0 == 0 && ncols == n && prm.simple_steps;
+    bool symmetric = sym_allowed && col0 == 0 && ncols == n && prm.simple_steps;
+    if (symmetric) {  // the per-tile row-sum slots must stay a modest part of the device memory
+      size_t free_b = 0, total_b = 0;
+      B200W_CUDA(cudaMemGetInfo(&free_b, &total_b));
+      if ((size_t)sym_offset(CT) * Pc * kBM * sizeof(double) > total_b / 8) symmetric = false;
+    }
     const int64_t T = symmetric ? sym_offset(CT) : CT * RT;
     const int G = (int)(T < resident ? T : resident);  // persistent: two CTAs per SM, equal tile ranges
     int max_seg = 1;  // column tiles one CTA range can touch
