@@ -15,13 +15,22 @@
 // warps add acc * 256^(w - w_min) to a float64 running sum.  Integer accumulation has no rounding, so
 // the result does not depend on the order of K-blocks, on the tile schedule or on the number of GPUs.
 //
-// Kernel structure (persistent, one CTA per SM, 256 threads):
-//   warp 0   TMA producer: 4-stage ring of {A tile 128 x 128 B, B tile 256 x 128 B}, SWIZZLE_128B
-//   warp 1   MMA issuer: one lane issues tcgen05.mma M128 N256 K32, 4 per stage; tcgen05.commit frees
-//            the stage and, at the end of a pass, publishes the accumulator
-//   warp 2   TMEM allocator (512 columns = two 128 x 256 s32 accumulators, double buffered)
-//   warps 4-7 epilogue: tcgen05.ld 32 lanes x 32 columns, float64 running sum in an L2-resident per-CTA
-//            scratch (coalesced: lanes = rows), last pass applies (L + a) / (min(k_i,k_j) + 1 - a)
+// Kernel structure (persistent, one CTA per SM, 320 threads; tom_i8_kernel<2> pairs the CTAs of two SMs
+// into a cluster that works on one 256 x 256 tile with cta_group::2 MMAs, tom_i8_kernel<1> is the
+// single-CTA 128 x 256 form):
+//   warp 0     TMA producer: 6-stage ring of {row-operand tile 128 rows x 128 B, column-operand tile (half)
+//              x 128 B}, SWIZZLE_128B; meets the producers of all CTAs at a global counter before every
+//              digit-pair segment (split arrive / wait) so that co-resident CTAs keep sharing panels in L2
+//   warp 1     MMA issuer (leader CTA of a pair): one lane issues tcgen05.mma K32, 4 per stage;
+//              tcgen05.commit (multicast in a pair) frees the stage and, at the end of a pass, publishes
+//              the accumulator
+//   warp 2     also the TMEM allocator (512 columns = two s32 accumulators, double buffered)
+//   warps 4-7  epilogue: tcgen05.ld 32 lanes x 32 columns, float64 running sum of the passes in an
+//              L2-resident per-CTA scratch (two buffers)
+//   warps 2, 3, 8, 9  finalizers: when a tile's last pass is in they apply (L + a) / (min(k_i,k_j) + 1 - a)
+//              etc. and store the tile -- directly, mirrored (symmetric schedule: only tiles on and above the
+//              diagonal are computed), into a peer's HBM (sharded run) or in condensed order -- and count
+//              finished tiles per row block for a host that copies results out while the kernel runs
 #include <cuda.h>
 
 #include <algorithm>
