@@ -41,7 +41,7 @@ WORKLOADS = {
 }
 METRIC = "TOMsimilarity+softThreshold TFLOP/s (sweep + adjacency + TOM, algorithmic flops)"
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from `ncu --set full` (profiles/), per launch
-TRAFFIC = {("C2", "i8", 1): 90.96e9 + 11.37e9}  # profiles/r01_ncu_full_final_k4.txt
+TRAFFIC = {("C2", "i8", 1): 75.50e9 + 11.32e9}  # profiles/r01_ncu_full_final_step_kernels.txt (inside a bench step)
 
 
 def step_flops(m, n, P):
