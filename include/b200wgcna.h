@@ -58,7 +58,12 @@ extern "C" {
 #define B200W_PREC_AUTO 0    /* = B200W_PREC_I8 */
 #define B200W_PREC_F64 1     /* FP64 tensor-core DMMA (mma.sync f64)                    */
 #define B200W_PREC_I8 2      /* tcgen05 kind::i8, exact int32 accumulation of fixed-point
-                                digit slices (row-scaled, 5 slices = 39 bits)            */
+                                digit slices (row-scaled, 5 slices = 39 bits), the 15 digit-pair
+                                products of weight >= 4: max-abs error on TOM ~5e-12      */
+#define B200W_PREC_I8_FAST 3 /* the same planes, only the 10 digit-pair products of weight >= 5:
+                                2/3 of the tensor-core work, max-abs error on TOM ~1e-9 (the
+                                north-star tolerance is 1e-6); single-GPU entry points only,
+                                the sharded contraction always runs B200W_PREC_I8          */
 
 int b200w_version(void);
 const char* b200w_last_error(void);

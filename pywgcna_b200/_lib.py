@@ -19,7 +19,7 @@ NET_TYPES = ["unsigned", "signed", "signed hybrid"]  # wgcna.py:53-54
 TOM_TYPES = ["unsigned", "signed"]  # wgcna.py:55
 TOM_DENOMS = ["min", "mean"]  # wgcna.py:56
 OUT_TOM, OUT_DISS, OUT_DISS_R8, OUT_DISS_COND, OUT_DISS_R8_COND = 0, 1, 2, 3, 4
-PREC_AUTO, PREC_F64, PREC_I8 = 0, 1, 2
+PREC_AUTO, PREC_F64, PREC_I8, PREC_I8_FAST = 0, 1, 2, 3
 I8_SLICES = 5
 
 E_INVALID, E_NO_DEVICE, E_CUDA, E_NOMEM, E_UNSUPPORTED = -1, -2, -3, -4, -5

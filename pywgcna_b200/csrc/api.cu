@@ -17,7 +17,7 @@
 int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t op_rows, const double* d_scale,
                          const double* d_k, int64_t n, int64_t row0, int64_t nrows, int tom_type, int tom_denom,
                          int out_mode, double* d_out, cudaStream_t st, int world, int rank, int64_t per,
-                         double* const* peer_out, b200w::TomProgress* progress);
+                         double* const* peer_out, b200w::TomProgress* progress, int w_min);
 
 namespace b200w {
 
@@ -478,7 +478,7 @@ static int tom_from_device_adjacency(const double* dA, int64_t n, int tom_type, 
   if (int e = b200w_dev_tom_prepare(dA, n, 0, n, precision, dOp.p, op_rows, dScale.as<double>(),
                                     dK.as<double>(), device, s))
     return e;
-  if (precision == B200W_PREC_I8 && row0 == 0 && nrows == n && !condensed && !getenv("B200W_NO_OVERLAP")) {
+  if (prec_is_i8(precision) && row0 == 0 && nrows == n && !condensed && !getenv("B200W_NO_OVERLAP")) {
     // whole matrix on the tensor-core path: the kernel reports finished row blocks through host-mapped
     // flags and they are copied out on a second stream while later blocks are still being computed
     // (3.2 GB of D2H at C2 take 62 ms, the kernel 35 ms: the copy hides the kernel, not the reverse)
@@ -486,7 +486,8 @@ static int tom_from_device_adjacency(const double* dA, int64_t n, int tom_type, 
       return fail(B200W_E_INVALID, "tom: bad enum");
     TomProgress prog;
     if (int e = b200w_tom_compute_i8(dA, dOp.p, op_rows, dScale.as<double>(), dK.as<double>(), n, 0, n, tom_type,
-                                     tom_denom, out_mode, dOut.as<double>(), s, 1, 0, 0, nullptr, &prog))
+                                     tom_denom, out_mode, dOut.as<double>(), s, 1, 0, 0, nullptr, &prog,
+                                     prec_w_min(precision)))
       return e;
     if (prog.nb > 0) {
       Stream s2;

@@ -18,6 +18,9 @@ int ensure_device(int device);  // cudaSetDevice + sm_100 check; 0 or negative c
 extern std::atomic<long long> g_launches;
 extern double g_last_kernel_ms;
 int resolve_precision(int precision);  // B200W_PREC_AUTO -> the default contraction arithmetic
+inline bool prec_is_i8(int precision) { return precision == B200W_PREC_I8 || precision == B200W_PREC_I8_FAST; }
+// lowest digit-pair weight kept by the int8 contraction (tom_i8.cu) for a resolved precision
+inline int prec_w_min(int precision) { return precision == B200W_PREC_I8_FAST ? B200W_I8_SLICES : B200W_I8_SLICES - 1; }
 
 #define B200W_CUDA(expr)                                                                    \
   do {                                                                                      \

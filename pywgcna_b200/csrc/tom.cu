@@ -210,7 +210,8 @@ int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t o
                          const double* d_scale,
                          const double* d_k, int64_t n, int64_t row0, int64_t nrows, int tom_type,
                          int tom_denom, int out_mode, double* d_out, cudaStream_t st, int world,
-                         int rank, int64_t per, double* const* peer_out, b200w::TomProgress* progress);
+                         int rank, int64_t per, double* const* peer_out, b200w::TomProgress* progress,
+                         int w_min);
 
 int b200w::resolve_precision(int precision) {
   if (precision == B200W_PREC_AUTO) return B200W_PREC_I8;
@@ -233,7 +234,7 @@ extern "C" int b200w_dev_tom_prepare(const double* dA_rows, int64_t n, int64_t r
     B200W_LAUNCHED();
     return 0;
   }
-  if (precision == B200W_PREC_I8) {
+  if (prec_is_i8(precision)) {
     if (!d_scale) return fail(B200W_E_INVALID, "tom_prepare: i8 needs d_scale");
     return b200w_tom_prepare_i8(dA_rows, n, row0, nrows, d_operand, op_rows, d_scale, d_k, st);
   }
@@ -269,10 +270,10 @@ extern "C" int b200w_dev_tom_compute(const double* dA_rows, const void* d_operan
     B200W_LAUNCHED();
     return 0;
   }
-  if (precision == B200W_PREC_I8) {
+  if (prec_is_i8(precision)) {
     if (!d_scale) return fail(B200W_E_INVALID, "tom_compute: i8 needs d_scale");
     return b200w_tom_compute_i8(dA_rows, d_operand, op_rows, d_scale, d_k, n, row0, nrows, tom_type,
-                                tom_denom, out_mode, d_out, st, 1, 0, 0, nullptr, nullptr);
+                                tom_denom, out_mode, d_out, st, 1, 0, 0, nullptr, nullptr, prec_w_min(precision));
   }
   return fail(B200W_E_INVALID, "tom_compute: unknown precision %d", precision);
 }
@@ -297,7 +298,7 @@ extern "C" int b200w_dev_tom_compute_dist(const double* dA_rows, const void* d_o
     if (!peer_out[r] && (int64_t)r * per < n) return fail(B200W_E_INVALID, "tom_compute_dist: peer_out[%d] is NULL", r);
   return b200w_tom_compute_i8(dA_rows, d_operand, op_rows, d_scale, d_k, n, row0, nrows, tom_type,
                               tom_denom, out_mode, (double*)peer_out[rank], (cudaStream_t)stream, world,
-                              rank, per, (double* const*)peer_out, nullptr);
+                              rank, per, (double* const*)peer_out, nullptr, prec_w_min(B200W_PREC_I8));
 }
 
 int b200w_dev_intramodular(const double* dA, int64_t n, const int32_t* d_labels,

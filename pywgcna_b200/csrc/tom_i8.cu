@@ -47,6 +47,7 @@ constexpr int kTM = 128, kTN = 256, kKB = 128;  // tile rows, tile cols, K bytes
 constexpr int kMaxSegs = 96, kMaxPasses = 48;
 constexpr int kI8Threads = 320;  // warps: 0 TMA, 1 MMA, 2-3 + 8-9 finalizers (2 also owns TMEM), 4-7 epilogue
 constexpr int kMaxKbPerPass = 1023;
+constexpr int kCtasDefaultLead = 6;  // = ring stages of the 2-CTA kernel
 
 struct Seg {
   int16_t s, t;    // digit planes of the left (row) and right (column) operand
@@ -75,7 +76,8 @@ struct I8Params {
   unsigned int* prog_flag;            //           host-mapped flags, set to 1 when a block is complete
   int32_t prog_tiles;                 //           row tiles (of 256 rows) per row block
   int32_t fin_warps;       // finalizer warps per CTA: 4 (warps 2, 3, 8, 9; measured best) or 2 (warps 2, 3)
-  int32_t sync_mode;       // 0 none, 1 grid barrier of the producers per tile, 2 per segment
+  int32_t sync_mode;       // 0 none, 1 grid barrier of the producers per tile, 2 per segment, 3 split (default)
+  int32_t sync_lead;       // split barrier: K-blocks before a segment's end at which the next arrival is posted
   unsigned int* sync_ctr;  // zeroed before launch
   double final_scale;    // 256^w_min
   Seg seg[kMaxSegs];
@@ -405,7 +407,7 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
             if (split) atomicAdd(p.sync_ctr, 1u);  // arrival for the next segment
             continue;
           }
-          const int arrive_kb = (sgm.kb1 - kStages > sgm.kb0) ? sgm.kb1 - kStages : sgm.kb0;
+          const int arrive_kb = (sgm.kb1 - p.sync_lead > sgm.kb0) ? sgm.kb1 - p.sync_lead : sgm.kb0;
           for (int kb = sgm.kb0; kb < sgm.kb1; ++kb) {
             if (split && kb == arrive_kb) atomicAdd(p.sync_ctr, 1u);  // arrival for the next segment
             mbar_wait(&bars->empty[stage], phase ^ 1);
@@ -714,7 +716,7 @@ int b200w_tom_prepare_i8(const double* dA_rows, int64_t n, int64_t row0, int64_t
 int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t op_rows, const double* d_scale,
                          const double* d_k, int64_t n, int64_t row0, int64_t nrows, int tom_type, int tom_denom,
                          int out_mode, double* d_out, cudaStream_t st, int world, int rank, int64_t per,
-                         double* const* peer_out, b200w::TomProgress* progress) {
+                         double* const* peer_out, b200w::TomProgress* progress, int w_min_arg) {
   const int64_t ldn = b200w_padded_n(n);
   if (op_rows > 0x7fffffff || ldn > 0x7fffffff) return fail(B200W_E_UNSUPPORTED, "tom_i8: n too large");
   EncodeTiledFn encode = get_encode_tiled();
@@ -745,7 +747,7 @@ int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t o
   prm.out_mode = out_mode;
   prm.group = 8;
   if (const char* e = getenv("B200W_I8_GROUP")) prm.group = atoi(e) > 0 ? atoi(e) : 8;
-  int w_min = kS - 1;
+  int w_min = w_min_arg > 0 ? w_min_arg : kS - 1;
   if (const char* e = getenv("B200W_I8_WMIN")) w_min = atoi(e);
   if (w_min < 0 || w_min > 2 * (kS - 1)) return fail(B200W_E_INVALID, "tom_i8: bad B200W_I8_WMIN");
   if (build_schedule(prm, (int)(ldn / kKB), w_min))
@@ -836,6 +838,8 @@ int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t o
   if (const char* e = getenv("B200W_I8_FIN")) prm.fin_warps = atoi(e) == 2 ? 2 : 4;
   prm.sync_mode = 3;
   if (const char* e = getenv("B200W_I8_SYNC")) prm.sync_mode = atoi(e);
+  prm.sync_lead = kCtasDefaultLead;
+  if (const char* e = getenv("B200W_I8_LEAD")) prm.sync_lead = atoi(e) > 0 ? atoi(e) : kCtasDefaultLead;
   if (progress != nullptr) {
     progress->nb = 0;
     if (symmetric && !dist && !out_is_condensed(out_mode)) {

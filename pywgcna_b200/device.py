@@ -48,7 +48,7 @@ class DeviceNetwork:
         torch.cuda.set_device(self.device)
         self.dev = torch.device("cuda", self.device)
         self.net = L.NET_TYPES.index(networkType)
-        self.prec = {"auto": L.PREC_AUTO, "f64": L.PREC_F64, "i8": L.PREC_I8}[precision]
+        self.prec = {"auto": L.PREC_AUTO, "f64": L.PREC_F64, "i8": L.PREC_I8, "i8-fast": L.PREC_I8_FAST}[precision]
         self.group = group
         self.use_dist = use_dist  # torch.distributed collectives (False: the caller moves the blocks, tests)
         if world is None:

@@ -46,10 +46,10 @@ ENDC = "\033[0m"
 
 #: set to False to silence the progress prints the reference emits
 VERBOSE = os.environ.get("B200WGCNA_QUIET", "") == ""
-#: arithmetic of the TOM contraction: "auto" | "f64" | "i8" (see B200W_PREC_* in the header)
+#: arithmetic of the TOM contraction: "auto" | "f64" | "i8" | "i8-fast" (see B200W_PREC_* in the header)
 PRECISION = os.environ.get("B200WGCNA_PRECISION", "auto")
 
-_PREC = {"auto": L.PREC_AUTO, "f64": L.PREC_F64, "i8": L.PREC_I8}
+_PREC = {"auto": L.PREC_AUTO, "f64": L.PREC_F64, "i8": L.PREC_I8, "i8-fast": L.PREC_I8_FAST}
 
 
 def _say(*a, **k):

@@ -380,6 +380,29 @@ def test_adjacency_from_sweep_similarity(gpu, net, n, power):
             assert np.array_equal(part.adjacency(power).cpu().numpy(), A0[rows], equal_nan=True)
 
 
+@pytest.mark.parametrize("n", [700, 2500])
+def test_int8_fast_precision(gpu, n):
+    """precision="i8-fast" (B200W_PREC_I8_FAST: the 10 digit-pair products of weight >= 5 instead of 15): well
+    inside the north-star tolerance of 1e-6 on TOM, exactly symmetric, and reachable through every single-GPU
+    entry point (host API, fused network call, device-resident chaining)."""
+    from pywgcna_b200.device import DeviceNetwork
+
+    X = make_expression(50, n, F=6, seed=17 * n)
+    df = pd.DataFrame(X)
+    A = bw.adjacency(df, adjacencyType="signed hybrid", power=6)
+    T0 = O.TOMsimilarity(A.copy(), TOMType="signed").to_numpy()
+    Tf = bw.TOMsimilarity(A.copy(), TOMType="signed", precision="i8-fast").to_numpy()
+    err_fast, err_i8 = maxabs(Tf, T0), maxabs(bw.TOMsimilarity(A.copy(), TOMType="signed", precision="i8").to_numpy(), T0)
+    print(f"n={n}: max-abs error i8 {err_i8:.2e}, i8-fast {err_fast:.2e}")
+    assert err_fast < 1e-7 and err_i8 < TOL_TOM["i8"]
+    assert np.array_equal(Tf, Tf.T)
+    _, Tn = bw.network(df, power=6, networkType="signed hybrid", TOMType="signed", precision="i8-fast")
+    assert np.array_equal(Tn.to_numpy(), Tf)
+    net = DeviceNetwork(X, device=0, networkType="signed hybrid", precision="i8-fast")
+    net.adjacency(6)
+    assert np.array_equal(net.tom(TOMType="signed").cpu().numpy(), Tf)
+
+
 @pytest.mark.parametrize("n,m", [(3, 4), (5, 9), (17, 4), (127, 9), (129, 4), (255, 9), (257, 4)])
 def test_tiny_and_ragged_sizes(gpu, n, m):
     """Sizes below / straddling every tile (128-row DMMA tiles, 256 x 256 tcgen05 tiles, 128-byte K blocks)."""
