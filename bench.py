@@ -245,18 +245,23 @@ def run_ours(args):
     prec_name = {L.PREC_F64: "f64", L.PREC_I8: "i8"}[
         L.PREC_F64 if lib.b200w_tom_operand_bytes(128, net_dev.prec) == 128 * 128 * 8 else L.PREC_I8]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    tom_events = []
+    tom_events, phase_events = [], []
     state = {}
 
     def step():
         if not os.environ.get("B200W_BENCH_NOFLUSH"):
             flush.zero_()  # L2 flush between steps (256 MiB > 126 MB L2); the big operands exceed L2 anyway
+        p0, p1, p2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        p0.record()
         net_dev.standardize()
         # sweep -> per-power histograms / medians / exact sums on the device -> the whole sft table of
         # wgcna.py:924-932 (two 10-point regressions per power on the host) -> power selection :945-953
         power, _table = net_dev.sft(powers, nBreaks=10, RsquaredCut=0.9, MeanCut=100)
         power = int(power)
+        p1.record()
         net_dev.adjacency(power)
+        p2.record()
+        phase_events.append((p0, p1, p2))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         # events around the contraction only: prepare + exchange happen inside tom() before compute,
         # so bracket the whole call and subtract nothing -- the contraction dominates; the kernel-only
@@ -278,6 +283,7 @@ def run_ours(args):
         step()
     barrier()
     tom_events.clear()
+    phase_events.clear()
     try:
         uuid = str(torch.cuda.get_device_properties(local).uuid)
     except Exception:
@@ -303,6 +309,11 @@ def run_ours(args):
     ms_step = float(t.item()) / args.steps
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     tom_ms = float(np.mean([a.elapsed_time(b) for a, b in tom_events]))
+    # where a step's time goes (device timeline; the soft-threshold phase includes the host's 2 x P regressions,
+    # during which the GPU waits for the selected power)
+    phases = {"soft_threshold": float(np.mean([a.elapsed_time(b) for a, b, _ in phase_events])),
+              "adjacency": float(np.mean([b.elapsed_time(c) for _, b, c in phase_events])),
+              "tom": tom_ms}
 
     # dominant kernel alone (the A.A contraction + TOM epilogue): CUDA events on the launching stream
     from pywgcna_b200.shard import symmetric_tile_count
@@ -430,7 +441,7 @@ def run_ours(args):
                        "TOMType": tom_type, "TOMDenom": "min", "selected_power": state["power"],
                        "tom_precision": prec_name, "l2": "256 MiB flush each step; operands (3.2 GB+) exceed L2",
                        "parallelism": f"row-block x{world}"},
-            "clocks": clocks, "gpu_launches": int(launches), "tom_ms_in_step": tom_ms,
+            "clocks": clocks, "gpu_launches": int(launches), "tom_ms_in_step": tom_ms, "phases_ms": phases,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         }
         print(json.dumps(line), flush=True)
