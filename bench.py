@@ -37,6 +37,7 @@ WORKLOADS = {
     "C2": (200, 20000, 40, 20200, "signed hybrid", "signed", list(range(1, 21))),
     "C3": (500, 50000, 60, 50500, "unsigned", "unsigned", list(range(1, 21))),
     "C4": (5000, 30000, 60, 305000, "signed", "signed", list(range(1, 21))),
+    "C5": (300, 80000, 80, 80300, "unsigned", "unsigned", list(range(1, 21))),
     "tiny": (60, 1500, 6, 7, "signed hybrid", "signed", list(range(1, 21))),
 }
 METRIC = "TOMsimilarity+softThreshold TFLOP/s (sweep + adjacency + TOM, algorithmic flops)"
