@@ -18,13 +18,13 @@ if sys.argv[1] == "gpu":
     df = pd.DataFrame(g["X"])
     p, _ = bw.pickSoftThreshold(df, networkType="signed hybrid", powerVector=list(g["powers"]))
     A = bw.adjacency(df, adjacencyType="signed hybrid", power=p)
-    for prec in ("i8", "f64"):
+    for prec in ("i8", "i8-fast", "f64"):
         np.save(os.path.join(out, f"e2e_tom_{prec}.npy"), bw.TOMsimilarity(A.copy(), TOMType="signed", precision=prec).to_numpy())
     print("power", int(p), "golden", int(g["power"]))
 else:
     from oracle import ref_import as R
     res = {}
-    for prec in ("i8", "f64"):
+    for prec in ("i8", "i8-fast", "f64"):
         T = np.load(os.path.join(out, f"e2e_tom_{prec}.npy"))
         labels, Z = R.ref_modules_from_tom(T, minClusterSize=30)
         res[prec] = {"labels_identical": bool(np.array_equal(labels, g["labels"])), "n_genes": int(len(labels)),
