@@ -102,3 +102,70 @@ def test_install_rebinds_static_methods():
     assert Dummy.pickSoftThreshold is bw.pickSoftThreshold
     bw.uninstall(Dummy)
     assert Dummy.TOMsimilarity() == "ref" and Dummy.adjacency() == "ref"
+
+
+def _emulate_device_stats(K, nBreaks):
+    """numpy stand-in for b200w_dev_sft_stats: per power min / max / median / plain sum / pd.cut counts and bin sums,
+    and the exact mantissa sums per frexp exponent as the (lo, hi) pairs the kernel hands over (value lo + hi * 2^27,
+    however the kernel splits the 53-bit mantissas internally)."""
+    P, n = K.shape
+    E, bias = 2304, 1100
+    stats = np.zeros((P, 4 + 2 * nBreaks))
+    buck = np.zeros((P, E, 2), dtype=np.int64)
+    for p in range(P):
+        k = K[p]
+        mn, mx = k.min(), k.max()
+        edges = W._cut_edges(float(mn), float(mx), nBreaks)
+        b = np.searchsorted(edges, k, side="left") - 1  # right-closed bins
+        for i in range(nBreaks):
+            stats[p, 4 + i] = (b == i).sum()
+            stats[p, 4 + nBreaks + i] = k[b == i].sum()
+        stats[p, :4] = mn, mx, statistics.median(k.tolist()), k.sum()
+        nz = k[(k != 0) & np.isfinite(k)]
+        m, e = np.frexp(nz)
+        M = (m * 2.0 ** 53).astype(np.int64)  # exact
+        # a different split than two 27-bit halves, to pin the (lo, hi) convention rather than one split
+        pieces = [np.sign(M) * ((np.abs(M) >> (11 * q)) & 0x7FF) for q in range(5)]
+        sums = [np.zeros(E, dtype=np.int64) for _ in range(5)]
+        for q in range(5):
+            np.add.at(sums[q], e + bias, pieces[q])
+        buck[p, :, 0] = sums[0] + (sums[1] << 11) + (sums[2] << 22)
+        buck[p, :, 1] = (sums[3] << 6) + (sums[4] << 17)
+    return stats, buck
+
+
+def test_fit_table_from_device_statistics_layout():
+    """Host half of the device-resident pickSoftThreshold (DeviceNetwork.sft / b200w_soft_threshold_stats): the
+    table assembled from per-power statistics equals the one computed from k itself -- mean, median, max bit for
+    bit (statistics.mean is the correctly rounded exact mean), regressions to rounding."""
+    rng = np.random.default_rng(11)
+    n, nb = 3001, 10
+    K = np.abs(rng.standard_normal((6, n))) * np.logspace(1.5, -7, 6)[:, None]
+    K[2, 5] = 0.0  # zeros are skipped by the mantissa sums and sit in the lowest bin
+    K[4] = np.round(K[4], 3) + 1e-3  # ties and an even spread over few distinct values
+    stats, buck = _emulate_device_stats(K, nb)
+    r2, slope, r2adj, mean, med, mx = W.fit_table_from_stats(stats, buck, n, nb)
+    r2_0, slope_0, r2adj_0, mean_0, med_0, mx_0 = W.fit_table(K, nb)
+    assert np.array_equal(mean, mean_0) and np.array_equal(med, med_0) and np.array_equal(mx, mx_0)
+    for i in range(K.shape[0]):
+        assert mean[i] == statistics.mean(K[i].tolist())
+    np.testing.assert_allclose(r2, r2_0, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(slope, slope_0, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(r2adj, r2adj_0, rtol=1e-9, atol=1e-11)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) on the smallest workload."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "tiny",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "TFLOP/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["config"]["workload"].startswith("tiny") or "tiny" in json.dumps(line["config"])
