@@ -102,17 +102,24 @@ int b200w_soft_threshold_stats(const double* X, int64_t m, int64_t n, const doub
 int b200w_adjacency(const double* X, int64_t m, int64_t n, int net_type, double power,
                     int64_t row0, int64_t nrows, double* A_out, int device);
 
-/* The three reductions WGCNA.checkAdjMat needs, wgcna.py:1135-1138, in one pass over A.
+/* The three reductions WGCNA.checkAdjMat needs, wgcna.py:1135-1138, in one pass over A.  stats holds SIX doubles:
  *   stats[0] = max |A - A^T| over non-NaN pairs, stats[1] = min, stats[2] = max (NaN ignored),
  *   stats[3] = number of NaN entries (numpy's max/min return NaN if any is present, which
- *   makes every check of the reference pass; the host logic reproduces that). */
+ *   makes every check of the reference pass; the host logic reproduces that),
+ *   stats[4] = max |A - A^T| after nan_to_num (what TomSimilarityFromAdj is handed by TOMsimilarity, :1185),
+ *   stats[5] = number of (i, j) whose NaN-ness differs from (j, i). */
 int b200w_check_adjacency(const double* A, int64_t n, double* stats, int device);
 
 /* WGCNA.TOMsimilarity / TomSimilarityFromAdj, wgcna.py:1185 (NaN -> 0), :1143 (diag <- 0),
  * :1145 (A @ A), :1146-1151 (k, min/mean denominator), :1153/:1155, :1156 (diag <- 1).
  * The input is not modified.  out is the nrows x n row block.
- * With check != 0 the checkAdjMat reductions run first on the device copy (stats4 as in
- * b200w_check_adjacency, may be NULL) and the call returns, without computing,
+ * The contraction is L = A @ A with k_i = row sums and k_j = COLUMN sums (:1145-1147): a matrix that is
+ * symmetric to 1e-12 (everything checkAdjMat lets through without a NaN) runs the mirrored schedule on one
+ * operand, any other takes its column operand from A^T.
+ * check == 0 is TomSimilarityFromAdj called directly: no nan_to_num, so a NaN makes every entry of its row
+ * and of its column NaN (diagonal 1), exactly as numpy's A @ A and plain sums do.
+ * With check != 0 (TOMsimilarity) the checkAdjMat reductions decide first (stats4 = the first four values
+ * of b200w_check_adjacency, may be NULL) and the call returns, without computing,
  *   B200W_CHECK_ASYMMETRIC  if max|A - A^T| > 1e-12                     (wgcna.py:1135)
  *   B200W_CHECK_RANGE       if min(A) < lo or max(A) > 1, lo = -1 for the signed TOM else 0 (:1137)
  * -- unless A holds a NaN, which makes both numpy comparisons of the reference False. */
@@ -185,7 +192,7 @@ int b200w_dev_sft_stats(const double* d_k, int P, int64_t n, int64_t ldk, int nb
 int b200w_dev_adjacency(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t n, int net_type,
                         double power, int64_t row0, int64_t nrows, double* dA, int device,
                         void* stream);
-int b200w_dev_check_adjacency(const double* dA, int64_t n, double* d_stats4, int device,
+int b200w_dev_check_adjacency(const double* dA, int64_t n, double* d_stats6, int device,
                               void* stream);
 
 /* TOM on device-resident data, three steps so that a multi-GPU caller can exchange the
@@ -235,6 +242,12 @@ int b200w_dev_free(void* p, int device);
 int b200w_ipc_export(void* p, unsigned char* handle64);
 int b200w_ipc_open(const unsigned char* handle64, int device, void** out);
 int b200w_ipc_close(void* p, int device);
+
+/* Host <-> device copies for callers that keep the chain on the device (DeviceNetwork) but hand results to
+ * numpy: DMA into / out of a caller buffer (page-locked for the duration of the call unless it already is,
+ * e.g. a b200w_host_alloc buffer); the call returns when the copy is complete. */
+int b200w_dev_download(void* host_dst, const void* dev_src, int64_t bytes, int device, void* stream);
+int b200w_dev_upload(void* dev_dst, const void* host_src, int64_t bytes, int device, void* stream);
 
 /* ----------------------------------------------------------------------- introspection */
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */

@@ -44,6 +44,38 @@ def case_pipeline(name, X, powers, tom_power=6):
     print(name, {k: np.shape(v) for k, v in out.items() if k.startswith(("sft", "power"))})
 
 
+def case_tom_from_adj():
+    """TomSimilarityFromAdj called directly (wgcna.py:1141-1157: no checks, no nan_to_num) and TOMsimilarity
+    on matrices that a NaN waves through checkAdjMat (:1135-1138 compare against NaN): asymmetric input
+    (A @ A, column sums k_j) and NaN propagation."""
+    W = R.load_reference()
+    rng = np.random.default_rng(707)
+    n = 131
+    out = {}
+    B = rng.uniform(0, 1, size=(n, n)) ** 3
+    asym = B.copy()                                   # plainly asymmetric
+    sym = (B + B.T) / 2
+    sym_nan = sym.copy()
+    sym_nan[7, 100] = sym_nan[100, 7] = np.nan        # symmetric NaN pattern
+    sym_nan[90, 90] = np.nan                          # a NaN on the diagonal is zeroed first (:1143)
+    asym_nan = sym.copy()
+    asym_nan[3, 50] = np.nan                          # NaN in (3, 50) only, and a 0 opposite it
+    asym_nan[50, 3] = 0.0
+    asym_nan[110, 111] += 0.25                        # and a real asymmetry
+    signed = (rng.uniform(-1, 1, size=(n, n)))        # asymmetric with negative entries (signed formula)
+    for nm, A in (("asym", asym), ("sym_nan", sym_nan), ("asym_nan", asym_nan), ("signed_asym", signed)):
+        out[f"A_{nm}"] = A
+        for tt, td in ((0, 0), (1, 1)):
+            with np.errstate(all="ignore"):
+                out[f"fromadj_{nm}_{tt}_{td}"] = W.WGCNA.TomSimilarityFromAdj(A.copy(), td, tt)
+    # the checked entry point: NaN -> checks pass vacuously -> nan_to_num -> asymmetric contraction
+    for nm in ("sym_nan", "asym_nan"):
+        for tt in ("unsigned", "signed"):
+            out[f"tomsim_{nm}_{tt}"] = R.ref_TOMsimilarity(out[f"A_{nm}"], TOMType=tt).to_numpy()
+    np.savez_compressed(os.path.join(OUT, "tom_from_adj.npz"), **out)
+    print("tom_from_adj", len(out), "arrays")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     # (1) planted modules, default power vector of WGCNA.__init__
@@ -106,4 +138,10 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    import sys
+
+    if len(sys.argv) > 1 and sys.argv[1] == "tom_from_adj":
+        case_tom_from_adj()
+    else:
+        main()
+        case_tom_from_adj()

@@ -33,7 +33,10 @@ import types
 import numpy as np
 import pandas as pd
 
-_REF_CANDIDATES = [os.environ.get("B200W_REF", ""), "/root/reference"]
+# $B200W_REF, the source tree of the build container, or the `pip install --target baseline/_ref` copy that
+# travels to the GPU box (git-ignored; __graft_entry__.build() creates it where /root/reference exists)
+_REF_CANDIDATES = [os.environ.get("B200W_REF", ""), "/root/reference",
+                   os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")]
 
 
 class _Stub(types.ModuleType):

@@ -75,6 +75,8 @@ SIGNATURES = {
     "b200w_ipc_export": (_int, [_dp, C.c_char_p]),
     "b200w_ipc_open": (_int, [C.c_char_p, _int, C.POINTER(C.c_void_p)]),
     "b200w_ipc_close": (_int, [_dp, _int]),
+    "b200w_dev_download": (_int, [_dp, _dp, _i64, _int, _dp]),
+    "b200w_dev_upload": (_int, [_dp, _dp, _i64, _int, _dp]),
     "b200w_launch_count": (_i64, []),
     "b200w_last_kernel_ms": (_dbl, []),
 }

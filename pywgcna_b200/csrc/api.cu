@@ -17,7 +17,8 @@
 int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t op_rows, const double* d_scale,
                          const double* d_k, int64_t n, int64_t row0, int64_t nrows, int tom_type, int tom_denom,
                          int out_mode, double* d_out, cudaStream_t st, int world, int rank, int64_t per,
-                         double* const* peer_out, b200w::TomProgress* progress, int w_min);
+                         double* const* peer_out, b200w::TomProgress* progress, int w_min,
+                         const b200w::TomColumnOperand* col);
 
 namespace b200w {
 
@@ -159,7 +160,20 @@ struct Stream {
   cudaStream_t s = nullptr;
   cudaError_t create() { return cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking); }
   ~Stream() {
-    if (s) cudaStreamDestroy(s);
+    if (s) {
+      cudaStreamSynchronize(s);  // an early error return must not leave copies in flight on recycled buffers
+      cudaStreamDestroy(s);
+    }
+  }
+};
+// Declared AFTER the buffers of a host entry point, so it runs before they are released: on an early
+// `return e` the work already queued on the call's stream is drained before DevBuf hands the memory back
+// to the cache (where the next call could reuse it on another stream) and HostPin unregisters the
+// caller's pages.  On the success path the stream is idle already and this costs nothing.
+struct StreamDrain {
+  cudaStream_t s;
+  ~StreamDrain() {
+    if (cudaStreamSynchronize(s) != cudaSuccess) cudaGetLastError();
   }
 };
 
@@ -321,6 +335,25 @@ extern "C" int b200w_ipc_close(void* p, int device) {
   return 0;
 }
 
+extern "C" int b200w_dev_download(void* host_dst, const void* dev_src, int64_t bytes, int device, void* stream) {
+  if (!host_dst || !dev_src || bytes < 0) return fail(B200W_E_INVALID, "dev_download: bad args");
+  if (int e = ensure_device(device)) return e;
+  HostPin pin;
+  pin.pin(host_dst, (size_t)bytes);  // no-op for a buffer of the pinned pool
+  B200W_CUDA(cudaMemcpyAsync(host_dst, dev_src, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  B200W_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+extern "C" int b200w_dev_upload(void* dev_dst, const void* host_src, int64_t bytes, int device, void* stream) {
+  if (!dev_dst || !host_src || bytes < 0) return fail(B200W_E_INVALID, "dev_upload: bad args");
+  if (int e = ensure_device(device)) return e;
+  HostPin pin;
+  pin.pin(host_src, (size_t)bytes);
+  B200W_CUDA(cudaMemcpyAsync(dev_dst, host_src, (size_t)bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  B200W_CUDA(cudaStreamSynchronize((cudaStream_t)stream));  // the caller's pages are unpinned on return
+  return 0;
+}
+
 extern "C" void* b200w_host_alloc(int64_t bytes) { return bytes < 0 ? nullptr : g_pool.alloc((size_t)bytes); }
 extern "C" void b200w_host_free(void* p) { g_pool.free(p); }
 extern "C" void b200w_host_trim(void) { g_pool.trim(); }
@@ -359,6 +392,7 @@ extern "C" int b200w_connectivity_sweep(const double* X, int64_t m, int64_t n, c
   Stream st;
   B200W_CUDA(st.create());
   DevBuf dX, dZ, dBad, dK;
+  StreamDrain drain{st.s};
   const int64_t ldk = b200w_padded_k(m);
   B200W_CUDA(dX.alloc((size_t)m * n * 8));
   B200W_CUDA(dZ.alloc((size_t)n * ldk * 8));
@@ -386,6 +420,7 @@ extern "C" int b200w_soft_threshold_stats(const double* X, int64_t m, int64_t n,
   Stream st;
   B200W_CUDA(st.create());
   DevBuf dX, dZ, dBad, dK, dS, dB;
+  StreamDrain drain{st.s};
   const int64_t ldk = b200w_padded_k(m);
   const size_t sbytes = (size_t)P * (4 + 2 * nbreaks) * 8;
   const size_t bbytes = (size_t)P * b200w_sft_exp_buckets() * 2 * 8;
@@ -421,6 +456,7 @@ extern "C" int b200w_adjacency(const double* X, int64_t m, int64_t n, int net_ty
   Trace tr("b200w_adjacency", st.s);
   DevBuf dX, dZ, dBad, dA;
   HostPin pin_out;
+  StreamDrain drain{st.s};
   pin_out.pin(A_out, (size_t)nrows * n * 8);
   tr.mark("pin");
   const int64_t ldk = b200w_padded_k(m);
@@ -450,11 +486,12 @@ extern "C" int b200w_check_adjacency(const double* A, int64_t n, double* stats, 
   Stream st;
   B200W_CUDA(st.create());
   DevBuf dA, dS;
+  StreamDrain drain{st.s};
   B200W_CUDA(dA.alloc((size_t)n * n * 8));
-  B200W_CUDA(dS.alloc(4 * 8));
+  B200W_CUDA(dS.alloc(6 * 8));
   B200W_CUDA(cudaMemcpyAsync(dA.p, A, (size_t)n * n * 8, cudaMemcpyHostToDevice, st.s));
   if (int e = b200w_dev_check_adjacency(dA.as<double>(), n, dS.as<double>(), device, st.s)) return e;
-  B200W_CUDA(cudaMemcpyAsync(stats, dS.p, 4 * 8, cudaMemcpyDeviceToHost, st.s));
+  B200W_CUDA(cudaMemcpyAsync(stats, dS.p, 6 * 8, cudaMemcpyDeviceToHost, st.s));
   B200W_CUDA(cudaStreamSynchronize(st.s));
   return 0;
 }
@@ -462,8 +499,10 @@ extern "C" int b200w_check_adjacency(const double* A, int64_t n, double* stats, 
 // shared tail of b200w_tom / b200w_network: dA holds the full n x n adjacency on the device
 static int tom_from_device_adjacency(const double* dA, int64_t n, int tom_type, int tom_denom,
                                      int out_mode, int precision, int64_t row0, int64_t nrows,
-                                     double* out_host, int device, cudaStream_t s) {
-  DevBuf dOp, dScale, dK, dOut;
+                                     double* out_host, int device, cudaStream_t s, bool asymmetric = false,
+                                     int nan_mode = 0) {
+  DevBuf dOp, dScale, dK, dOut, dAt, dOpT, dScaleT, dKT;
+  StreamDrain drain{s};
   precision = resolve_precision(precision);
   B200W_CUDA(dOp.alloc((size_t)b200w_tom_operand_bytes(n, precision)));
   B200W_CUDA(dScale.alloc((size_t)round_up(n, 128) * 8));
@@ -475,10 +514,35 @@ static int tom_from_device_adjacency(const double* dA, int64_t n, int tom_type, 
   const size_t out_bytes = condensed ? (size_t)n * (n - 1) / 2 * 8 : (size_t)nrows * n * 8;
   B200W_CUDA(dOut.alloc(out_bytes));
   const int64_t op_rows = round_up(n, 128);
-  if (int e = b200w_dev_tom_prepare(dA, n, 0, n, precision, dOp.p, op_rows, dScale.as<double>(),
-                                    dK.as<double>(), device, s))
+  if (int e = tom_prepare_impl(dA, n, 0, n, precision, dOp.p, op_rows, dScale.as<double>(), dK.as<double>(),
+                               device, s, nan_mode))
     return e;
-  if (prec_is_i8(precision) && row0 == 0 && nrows == n && !condensed && !getenv("B200W_NO_OVERLAP")) {
+  // The kernels contract rows with rows and mirror tiles, which is A @ A only for a symmetric A.  An
+  // adjacency that is not (TomSimilarityFromAdj takes anything; a NaN waves any matrix through
+  // checkAdjMat) gets its column operand from A^T: L = A @ A, k_j = column sums (wgcna.py:1145-1147).
+  TomColumnOperand col;
+  col.nan_mode = nan_mode;
+  if (asymmetric) {
+    B200W_CUDA(dAt.alloc((size_t)n * n * 8));
+    B200W_CUDA(dOpT.alloc((size_t)b200w_tom_operand_bytes(n, precision)));
+    B200W_CUDA(dScaleT.alloc((size_t)round_up(n, 128) * 8));
+    B200W_CUDA(dKT.alloc((size_t)round_up(n, 128) * 8));
+    B200W_CUDA(cudaMemsetAsync(dOpT.p, 0, (size_t)b200w_tom_operand_bytes(n, precision), s));
+    if (int e = tom_transpose(dA, n, dAt.as<double>(), s)) return e;
+    if (int e = tom_prepare_impl(dAt.as<double>(), n, 0, n, precision, dOpT.p, op_rows, dScaleT.as<double>(),
+                                 dKT.as<double>(), device, s, nan_mode))
+      return e;
+    col.operand = dOpT.p;
+    col.scale = dScaleT.as<double>();
+    col.k = dKT.as<double>();
+  } else {
+    col.operand = dOp.p;
+    col.scale = dScale.as<double>();
+    col.k = dK.as<double>();
+  }
+  const TomColumnOperand* colp = (asymmetric || nan_mode) ? &col : nullptr;
+  if (prec_is_i8(precision) && row0 == 0 && nrows == n && !condensed && !asymmetric &&
+      !getenv("B200W_NO_OVERLAP")) {
     // whole matrix on the tensor-core path: the kernel reports finished row blocks through host-mapped
     // flags and they are copied out on a second stream while later blocks are still being computed
     // (3.2 GB of D2H at C2 take 62 ms, the kernel 35 ms: the copy hides the kernel, not the reverse)
@@ -487,7 +551,7 @@ static int tom_from_device_adjacency(const double* dA, int64_t n, int tom_type, 
     TomProgress prog;
     if (int e = b200w_tom_compute_i8(dA, dOp.p, op_rows, dScale.as<double>(), dK.as<double>(), n, 0, n, tom_type,
                                      tom_denom, out_mode, dOut.as<double>(), s, 1, 0, 0, nullptr, &prog,
-                                     prec_w_min(precision)))
+                                     prec_w_min(precision), colp))
       return e;
     if (prog.nb > 0) {
       Stream s2;
@@ -511,9 +575,8 @@ static int tom_from_device_adjacency(const double* dA, int64_t n, int tom_type, 
     B200W_CUDA(cudaStreamSynchronize(s));
     return 0;
   }
-  if (int e = b200w_dev_tom_compute(dA + row0 * n, dOp.p, op_rows, dScale.as<double>(),
-                                    dK.as<double>(), n, row0, nrows, tom_type, tom_denom, out_mode, precision,
-                                    dOut.as<double>(), device, s))
+  if (int e = tom_compute_impl(dA + row0 * n, dOp.p, op_rows, dScale.as<double>(), dK.as<double>(), n, row0,
+                               nrows, tom_type, tom_denom, out_mode, precision, dOut.as<double>(), device, s, colp))
     return e;
   B200W_CUDA(cudaMemcpyAsync(out_host, dOut.p, out_bytes, cudaMemcpyDeviceToHost, s));
   B200W_CUDA(cudaStreamSynchronize(s));
@@ -532,6 +595,7 @@ extern "C" int b200w_tom(const double* A, int64_t n, int tom_type, int tom_denom
   Trace tr("b200w_tom", st.s);
   DevBuf dA;
   HostPin pin_in, pin_out;
+  StreamDrain drain{st.s};
   pin_in.pin(A, (size_t)n * n * 8);
   pin_out.pin(out, (out_mode == B200W_OUT_DISS_COND || out_mode == B200W_OUT_DISS_R8_COND)
                        ? (size_t)n * (n - 1) / 2 * 8 : (size_t)nrows * n * 8);
@@ -540,23 +604,29 @@ extern "C" int b200w_tom(const double* A, int64_t n, int tom_type, int tom_denom
   tr.mark("alloc");
   B200W_CUDA(cudaMemcpyAsync(dA.p, A, (size_t)n * n * 8, cudaMemcpyHostToDevice, st.s));
   tr.mark("h2d");
-  if (check) {
+  // the checkAdjMat reductions run in every case: with check they decide (wgcna.py:1135-1138), without
+  // they only tell whether the matrix is symmetric enough for the mirrored schedule
+  double hs[6];
+  {
     DevBuf dS;
-    double hs[4];
-    B200W_CUDA(dS.alloc(4 * 8));
+    B200W_CUDA(dS.alloc(6 * 8));
     if (int e = b200w_dev_check_adjacency(dA.as<double>(), n, dS.as<double>(), device, st.s)) return e;
-    B200W_CUDA(cudaMemcpyAsync(hs, dS.p, 4 * 8, cudaMemcpyDeviceToHost, st.s));
+    B200W_CUDA(cudaMemcpyAsync(hs, dS.p, 6 * 8, cudaMemcpyDeviceToHost, st.s));
     B200W_CUDA(cudaStreamSynchronize(st.s));
-    if (stats4) for (int i = 0; i < 4; ++i) stats4[i] = hs[i];
-    if (hs[3] == 0.0) {  // any NaN makes np.max / np.min NaN and both comparisons False
-      if (hs[0] > 1e-12) return B200W_CHECK_ASYMMETRIC;
-      const double lo = (tom_type == B200W_TOM_SIGNED) ? -1.0 : 0.0;
-      if (hs[1] < lo || hs[2] > 1.0) return B200W_CHECK_RANGE;
-    }
+  }
+  if (stats4) for (int i = 0; i < 4; ++i) stats4[i] = hs[i];
+  if (check && hs[3] == 0.0) {  // any NaN makes np.max / np.min NaN and both comparisons False
+    if (hs[0] > 1e-12) return B200W_CHECK_ASYMMETRIC;
+    const double lo = (tom_type == B200W_TOM_SIGNED) ? -1.0 : 0.0;
+    if (hs[1] < lo || hs[2] > 1.0) return B200W_CHECK_RANGE;
   }
   tr.mark("check");
+  // check (TOMsimilarity): NaN -> 0 first (:1185), then TomSimilarityFromAdj on whatever that leaves.
+  // no check (TomSimilarityFromAdj called directly): NaNs stay and propagate like numpy's A @ A and sums.
+  const int nan_mode = (!check && hs[3] > 0.0) ? 1 : 0;
+  const bool asymmetric = hs[4] > 1e-12 || (nan_mode && hs[5] > 0.0);
   const int rc = tom_from_device_adjacency(dA.as<double>(), n, tom_type, tom_denom, out_mode, precision,
-                                           row0, nrows, out, device, st.s);
+                                           row0, nrows, out, device, st.s, asymmetric, nan_mode);
   tr.mark("prepare+contraction+d2h");
   return rc;
 }
@@ -570,6 +640,7 @@ extern "C" int b200w_network(const double* X, int64_t m, int64_t n, int net_type
   B200W_CUDA(st.create());
   DevBuf dX, dZ, dBad, dA;
   HostPin pin_a, pin_t;
+  StreamDrain drain{st.s};
   pin_a.pin(A_out, (size_t)n * n * 8);
   pin_t.pin(tom_out, (size_t)n * n * 8);
   const int64_t ldk = b200w_padded_k(m);
@@ -597,6 +668,7 @@ extern "C" int b200w_cross_correlation(const double* X, int64_t m, int64_t n, co
   Stream st;
   B200W_CUDA(st.create());
   DevBuf dX, dY, dZx, dZy, dBx, dBy, dC;
+  StreamDrain drain{st.s};
   const int64_t ldk = b200w_padded_k(m);
   B200W_CUDA(dX.alloc((size_t)m * n * 8));
   B200W_CUDA(dY.alloc((size_t)m * M * 8));
@@ -629,6 +701,7 @@ extern "C" int b200w_intramodular(const double* A, int64_t n, const int32_t* lab
   Stream st;
   B200W_CUDA(st.create());
   DevBuf dA, dL, dS, dT, dW;
+  StreamDrain drain{st.s};
   B200W_CUDA(dA.alloc((size_t)n * n * 8));
   B200W_CUDA(dL.alloc((size_t)n * 4));
   B200W_CUDA(dS.alloc((size_t)nmod));

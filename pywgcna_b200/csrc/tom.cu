@@ -8,7 +8,8 @@
 namespace b200w {
 
 // -------------------------------------------------------------------------------------------
-// checkAdjMat reductions (wgcna.py:1135-1138): max|A - A^T|, min, max, NaN count in one pass.
+// checkAdjMat reductions (wgcna.py:1135-1138): max|A - A^T|, min, max, NaN count in one pass, plus
+// max|A - A^T| of the matrix after nan_to_num (what TomSimilarityFromAdj really gets, :1185 -> :1189).
 // Each CTA handles one 32 x 32 tile pair (bi <= bj): it reads tile (bi,bj) and tile (bj,bi), both
 // row-wise (coalesced), transposes the second through shared memory.  Per-CTA partials are reduced
 // by a second kernel in fixed order.
@@ -16,7 +17,7 @@ namespace b200w {
 __global__ void __launch_bounds__(256)
 check_adj_kernel(const double* __restrict__ A, int64_t n, int64_t tiles, double* __restrict__ part) {
   __shared__ double tb[32][33];
-  __shared__ double red[4][8];
+  __shared__ double red[6][8];
   // triangular tile index -> (bi, bj), bi <= bj
   int64_t t = blockIdx.x;
   int64_t bi = (int64_t)floor((2.0 * tiles + 1.0 - sqrt((2.0 * tiles + 1.0) * (2.0 * tiles + 1.0) - 8.0 * (double)t)) / 2.0);
@@ -25,7 +26,7 @@ check_adj_kernel(const double* __restrict__ A, int64_t n, int64_t tiles, double*
   int64_t bj = bi + (t - (bi * tiles - bi * (bi - 1) / 2));
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
 
-  double asym = 0.0, mn = INFINITY, mx = -INFINITY, nans = 0.0;
+  double asym = 0.0, mn = INFINITY, mx = -INFINITY, nans = 0.0, asymc = 0.0, nanasym = 0.0;
   for (int r = ty; r < 32; r += 8) {  // tile (bj, bi) rows
     int64_t i = bj * 32 + r, j = bi * 32 + tx;
     tb[r][tx] = (i < n && j < n) ? A[i * n + j] : 0.0;
@@ -36,6 +37,8 @@ check_adj_kernel(const double* __restrict__ A, int64_t n, int64_t tiles, double*
     if (i < n && j < n) {
       double a = A[i * n + j], b = tb[tx][r];
       asym = fmax(asym, fabs(a - b));  // fmax drops a NaN operand
+      asymc = fmax(asymc, fabs((isnan(a) ? 0.0 : a) - (isnan(b) ? 0.0 : b)));  // after nan_to_num (wgcna.py:1185)
+      if (isnan(a) != isnan(b)) nanasym += 1.0;  // NaN pattern not symmetric
       if (isnan(a)) nans += 1.0; else { mn = fmin(mn, a); mx = fmax(mx, a); }
       if (bi != bj) { if (isnan(b)) nans += 1.0; else { mn = fmin(mn, b); mx = fmax(mx, b); } }
     }
@@ -45,36 +48,42 @@ check_adj_kernel(const double* __restrict__ A, int64_t n, int64_t tiles, double*
     mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
     mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     nans += __shfl_xor_sync(0xffffffffu, nans, o);
+    asymc = fmax(asymc, __shfl_xor_sync(0xffffffffu, asymc, o));
+    nanasym += __shfl_xor_sync(0xffffffffu, nanasym, o);
   }
-  if (tx == 0) { red[0][ty] = asym; red[1][ty] = mn; red[2][ty] = mx; red[3][ty] = nans; }
+  if (tx == 0) {
+    red[0][ty] = asym; red[1][ty] = mn; red[2][ty] = mx; red[3][ty] = nans; red[4][ty] = asymc;
+    red[5][ty] = nanasym;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int w = 1; w < 8; ++w) {
       asym = fmax(asym, red[0][w]); mn = fmin(mn, red[1][w]); mx = fmax(mx, red[2][w]);
-      nans += red[3][w];
+      nans += red[3][w]; asymc = fmax(asymc, red[4][w]); nanasym += red[5][w];
     }
-    double* o = part + (int64_t)blockIdx.x * 4;
-    o[0] = asym; o[1] = mn; o[2] = mx; o[3] = nans;
+    double* o = part + (int64_t)blockIdx.x * 6;
+    o[0] = asym; o[1] = mn; o[2] = mx; o[3] = nans; o[4] = asymc; o[5] = nanasym;
   }
 }
 
 __global__ void check_adj_reduce_kernel(const double* __restrict__ part, int64_t nb,
                                         double* __restrict__ stats) {
-  __shared__ double red[4][256];
-  double asym = 0.0, mn = INFINITY, mx = -INFINITY, nans = 0.0;
+  __shared__ double red[6][256];
+  double asym = 0.0, mn = INFINITY, mx = -INFINITY, nans = 0.0, asymc = 0.0, nanasym = 0.0;
   for (int64_t b = threadIdx.x; b < nb; b += blockDim.x) {
-    asym = fmax(asym, part[b * 4]); mn = fmin(mn, part[b * 4 + 1]);
-    mx = fmax(mx, part[b * 4 + 2]); nans += part[b * 4 + 3];
+    asym = fmax(asym, part[b * 6]); mn = fmin(mn, part[b * 6 + 1]);
+    mx = fmax(mx, part[b * 6 + 2]); nans += part[b * 6 + 3]; asymc = fmax(asymc, part[b * 6 + 4]);
+    nanasym += part[b * 6 + 5];
   }
   red[0][threadIdx.x] = asym; red[1][threadIdx.x] = mn; red[2][threadIdx.x] = mx;
-  red[3][threadIdx.x] = nans;
+  red[3][threadIdx.x] = nans; red[4][threadIdx.x] = asymc; red[5][threadIdx.x] = nanasym;
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int i = 1; i < (int)blockDim.x; ++i) {
       asym = fmax(asym, red[0][i]); mn = fmin(mn, red[1][i]); mx = fmax(mx, red[2][i]);
-      nans += red[3][i];
+      nans += red[3][i]; asymc = fmax(asymc, red[4][i]); nanasym += red[5][i];
     }
-    stats[0] = asym; stats[1] = mn; stats[2] = mx; stats[3] = nans;
+    stats[0] = asym; stats[1] = mn; stats[2] = mx; stats[3] = nans; stats[4] = asymc; stats[5] = nanasym;
   }
 }
 
@@ -84,19 +93,39 @@ __global__ void check_adj_reduce_kernel(const double* __restrict__ part, int64_t
 // -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 tom_prepare_f64_kernel(const double* __restrict__ A_rows, int64_t n, int64_t ldn, int64_t row0,
-                       double* __restrict__ Ac, double* __restrict__ k) {
+                       double* __restrict__ Ac, double* __restrict__ k, int nan_mode) {
   const int64_t i = row0 + blockIdx.x;
   const double* src = A_rows + (int64_t)blockIdx.x * n;
   double* dst = Ac + i * ldn;
-  double s = 0.0;
+  double s = 0.0, nn = 0.0;
   for (int64_t j = threadIdx.x; j < ldn; j += 256) {
     double a = 0.0;
-    if (j < n) a = tom_clean(src[j], i, j);
+    if (j < n) {
+      if (i != j && isnan(src[j])) nn += 1.0;
+      a = tom_clean(src[j], i, j);
+    }
     dst[j] = a;
     s += a;
   }
   s = block_sum_256(s);
-  if (threadIdx.x == 0) k[i] = s;
+  nn = block_sum_256(nn);
+  // nan_mode 1 (TomSimilarityFromAdj without the nan_to_num of TOMsimilarity): a NaN in the row makes its
+  // plain numpy sum NaN (wgcna.py:1146-1147) and the epilogue propagates it
+  if (threadIdx.x == 0) k[i] = (nan_mode && nn > 0.0) ? __longlong_as_double(0x7ff8000000000000LL) : s;
+}
+
+// At[j, i] = A[i, j]: the column operand of an asymmetric A (TomSimilarityFromAdj forms A @ A with the
+// column sums k_j, wgcna.py:1145-1147; the kernels contract rows with rows)
+__global__ void __launch_bounds__(256)
+transpose_kernel(const double* __restrict__ A, int64_t n, double* __restrict__ At) {
+  __shared__ double t[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t bi = (int64_t)blockIdx.y * 32, bj = (int64_t)blockIdx.x * 32;
+  for (int r = ty; r < 32; r += 8)
+    if (bi + r < n && bj + tx < n) t[r][tx] = A[(bi + r) * n + bj + tx];
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8)
+    if (bj + r < n && bi + tx < n) At[(bj + r) * n + bi + tx] = t[tx][r];
 }
 
 // -------------------------------------------------------------------------------------------
@@ -108,8 +137,9 @@ constexpr int kTomStages = 4;
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tom_f64_kernel(const double* __restrict__ A_rows, const double* __restrict__ Ac,
-               const double* __restrict__ k, int64_t n, int64_t ldn, int64_t row0, int64_t nrows,
-               int tom_type, int tom_denom, int out_mode, double* __restrict__ out) {
+               const double* __restrict__ Bc, const double* __restrict__ k,
+               const double* __restrict__ k_col, int nan_mode, int64_t n, int64_t ldn, int64_t row0,
+               int64_t nrows, int tom_type, int tom_denom, int out_mode, double* __restrict__ out) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, tig = lane & 3;
@@ -120,7 +150,8 @@ tom_f64_kernel(const double* __restrict__ A_rows, const double* __restrict__ Ac,
 
   AccF64 acc;
   acc.clear();
-  gemm_f64_tile<kTomStages>(acc, smem, Ac, Ac, ldn, ldn, i0, n, j0, n);
+  gemm_f64_tile<kTomStages>(acc, smem, Ac, Bc, ldn, ldn, i0, n, j0, n);
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
 #pragma unroll
   for (int mi = 0; mi < 4; ++mi) {
@@ -138,8 +169,9 @@ tom_f64_kernel(const double* __restrict__ A_rows, const double* __restrict__ Ac,
           const int64_t gj = j0 + wn * 32 + ni * 8 + 2 * tig + cb;
           if (gj >= n) continue;
           const double a = tom_clean(arow[gj], gi, gj);
-          const double t = tom_value(acc.v[mi][ni][ch * 2 + cb], a, ki, k[gj], gi == gj, tom_type,
-                                     tom_denom, out_mode);
+          const double kj = k_col[gj];
+          double t = tom_value(acc.v[mi][ni][ch * 2 + cb], a, ki, kj, gi == gj, tom_type, tom_denom, out_mode);
+          if (nan_mode && gi != gj && (isnan(ki) || isnan(kj) || isnan(arow[gj]))) t = qnan;
           if (!out_is_condensed(out_mode)) orow[gj] = t;
           else if (gj > gi) out[condensed_index(n, gi, gj)] = t;
         }
@@ -187,15 +219,16 @@ extern "C" int64_t b200w_tom_operand_bytes(int64_t n, int precision) {
   return (int64_t)B200W_I8_SLICES * rows * ldn;
 }
 
-extern "C" int b200w_dev_check_adjacency(const double* dA, int64_t n, double* d_stats4, int device,
+extern "C" int b200w_dev_check_adjacency(const double* dA, int64_t n, double* d_stats6, int device,
                                          void* stream) {
+  double* const d_stats4 = d_stats6;
   if (!dA || !d_stats4 || n < 1) return fail(B200W_E_INVALID, "check_adjacency: bad args");
   if (int e = ensure_device(device)) return e;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t tiles = (n + 31) / 32, nb = tiles * (tiles + 1) / 2;
   if (nb > 2147483647LL) return fail(B200W_E_UNSUPPORTED, "check_adjacency: n too large");
   Scratch part;
-  B200W_CUDA(part.alloc((size_t)nb * 4 * sizeof(double), st));
+  B200W_CUDA(part.alloc((size_t)nb * 6 * sizeof(double), st));
   check_adj_kernel<<<(unsigned)nb, 256, 0, st>>>(dA, n, tiles, part.as<double>());
   B200W_LAUNCHED();
   check_adj_reduce_kernel<<<1, 256, 0, st>>>(part.as<double>(), nb, d_stats4);
@@ -205,13 +238,13 @@ extern "C" int b200w_dev_check_adjacency(const double* dA, int64_t n, double* d_
 
 int b200w_tom_prepare_i8(const double* dA_rows, int64_t n, int64_t row0, int64_t nrows,
                          void* d_operand, int64_t op_rows, double* d_scale, double* d_k,
-                         cudaStream_t st);
+                         cudaStream_t st, int nan_mode);
 int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t op_rows,
                          const double* d_scale,
                          const double* d_k, int64_t n, int64_t row0, int64_t nrows, int tom_type,
                          int tom_denom, int out_mode, double* d_out, cudaStream_t st, int world,
                          int rank, int64_t per, double* const* peer_out, b200w::TomProgress* progress,
-                         int w_min);
+                         int w_min, const b200w::TomColumnOperand* col);
 
 int b200w::resolve_precision(int precision) {
   if (precision == B200W_PREC_AUTO) return B200W_PREC_I8;
@@ -221,6 +254,21 @@ int b200w::resolve_precision(int precision) {
 extern "C" int b200w_dev_tom_prepare(const double* dA_rows, int64_t n, int64_t row0, int64_t nrows,
                                      int precision, void* d_operand, int64_t op_rows,
                                      double* d_scale, double* d_k, int device, void* stream) {
+  return b200w::tom_prepare_impl(dA_rows, n, row0, nrows, precision, d_operand, op_rows, d_scale, d_k, device,
+                                 stream, 0);
+}
+
+int b200w::tom_transpose(const double* dA, int64_t n, double* dAt, cudaStream_t st) {
+  const int64_t t = (n + 31) / 32;
+  if (t > 65535) return fail(B200W_E_UNSUPPORTED, "tom: n too large for the transposed operand");
+  transpose_kernel<<<dim3((unsigned)t, (unsigned)t), 256, 0, st>>>(dA, n, dAt);
+  B200W_LAUNCHED();
+  return 0;
+}
+
+int b200w::tom_prepare_impl(const double* dA_rows, int64_t n, int64_t row0, int64_t nrows, int precision,
+                            void* d_operand, int64_t op_rows, double* d_scale, double* d_k, int device,
+                            void* stream, int nan_mode) {
   if (!dA_rows || !d_operand || !d_k || n < 1 || row0 < 0 || nrows < 1 || row0 + nrows > n)
     return fail(B200W_E_INVALID, "tom_prepare: bad args");
   if (op_rows < round_up(n, 128) || op_rows % 128)
@@ -230,13 +278,13 @@ extern "C" int b200w_dev_tom_prepare(const double* dA_rows, int64_t n, int64_t r
   cudaStream_t st = (cudaStream_t)stream;
   if (precision == B200W_PREC_F64) {
     tom_prepare_f64_kernel<<<(unsigned)nrows, 256, 0, st>>>(dA_rows, n, b200w_padded_n(n), row0,
-                                                            (double*)d_operand, d_k);
+                                                            (double*)d_operand, d_k, nan_mode);
     B200W_LAUNCHED();
     return 0;
   }
   if (prec_is_i8(precision)) {
     if (!d_scale) return fail(B200W_E_INVALID, "tom_prepare: i8 needs d_scale");
-    return b200w_tom_prepare_i8(dA_rows, n, row0, nrows, d_operand, op_rows, d_scale, d_k, st);
+    return b200w_tom_prepare_i8(dA_rows, n, row0, nrows, d_operand, op_rows, d_scale, d_k, st, nan_mode);
   }
   return fail(B200W_E_INVALID, "tom_prepare: unknown precision %d", precision);
 }
@@ -247,6 +295,14 @@ extern "C" int b200w_dev_tom_compute(const double* dA_rows, const void* d_operan
                                      int64_t row0, int64_t nrows, int tom_type, int tom_denom,
                                      int out_mode, int precision, double* d_out, int device,
                                      void* stream) {
+  return b200w::tom_compute_impl(dA_rows, d_operand, op_rows, d_scale, d_k, n, row0, nrows, tom_type, tom_denom,
+                                 out_mode, precision, d_out, device, stream, nullptr);
+}
+
+int b200w::tom_compute_impl(const double* dA_rows, const void* d_operand, int64_t op_rows, const double* d_scale,
+                            const double* d_k, int64_t n, int64_t row0, int64_t nrows, int tom_type,
+                            int tom_denom, int out_mode, int precision, double* d_out, int device, void* stream,
+                            const TomColumnOperand* col) {
   if (!dA_rows || !d_operand || !d_k || !d_out || n < 1 || row0 < 0 || nrows < 1 ||
       row0 + nrows > n)
     return fail(B200W_E_INVALID, "tom_compute: bad args");
@@ -265,15 +321,17 @@ extern "C" int b200w_dev_tom_compute(const double* dA_rows, const void* d_operan
                                     (int)smem));
     const int64_t tiles = ((nrows + kBM - 1) / kBM) * ((n + kBN - 1) / kBN);
     tom_f64_kernel<<<(unsigned)tiles, kGemmThreads, smem, st>>>(
-        dA_rows, (const double*)d_operand, d_k, n, b200w_padded_n(n), row0, nrows, tom_type,
-        tom_denom, out_mode, d_out);
+        dA_rows, (const double*)d_operand, col ? (const double*)col->operand : (const double*)d_operand, d_k,
+        col ? col->k : d_k, col ? col->nan_mode : 0, n, b200w_padded_n(n), row0, nrows, tom_type, tom_denom,
+        out_mode, d_out);
     B200W_LAUNCHED();
     return 0;
   }
   if (prec_is_i8(precision)) {
     if (!d_scale) return fail(B200W_E_INVALID, "tom_compute: i8 needs d_scale");
     return b200w_tom_compute_i8(dA_rows, d_operand, op_rows, d_scale, d_k, n, row0, nrows, tom_type,
-                                tom_denom, out_mode, d_out, st, 1, 0, 0, nullptr, nullptr, prec_w_min(precision));
+                                tom_denom, out_mode, d_out, st, 1, 0, 0, nullptr, nullptr, prec_w_min(precision),
+                                col);
   }
   return fail(B200W_E_INVALID, "tom_compute: unknown precision %d", precision);
 }
@@ -298,7 +356,7 @@ extern "C" int b200w_dev_tom_compute_dist(const double* dA_rows, const void* d_o
     if (!peer_out[r] && (int64_t)r * per < n) return fail(B200W_E_INVALID, "tom_compute_dist: peer_out[%d] is NULL", r);
   return b200w_tom_compute_i8(dA_rows, d_operand, op_rows, d_scale, d_k, n, row0, nrows, tom_type,
                               tom_denom, out_mode, (double*)peer_out[rank], (cudaStream_t)stream, world,
-                              rank, per, (double* const*)peer_out, nullptr, prec_w_min(B200W_PREC_I8));
+                              rank, per, (double* const*)peer_out, nullptr, prec_w_min(B200W_PREC_I8), nullptr);
 }
 
 int b200w_dev_intramodular(const double* dA, int64_t n, const int32_t* d_labels,

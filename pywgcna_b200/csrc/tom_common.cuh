@@ -12,6 +12,26 @@ struct TomProgress {
   int64_t rows_per_block = 0;
 };
 
+// Column operand of a contraction whose adjacency is NOT symmetric (TomSimilarityFromAdj on an unchecked
+// matrix, or TOMsimilarity on a matrix whose NaNs waved it through checkAdjMat): L = A @ A contracts the
+// rows of A with the rows of A^T, the denominator takes the column sums k_j (wgcna.py:1145-1147).
+// nan_mode != 0: no nan_to_num happened (TomSimilarityFromAdj called directly): entries whose row or
+// column holds a NaN come out NaN, as numpy's A @ A and plain sums make them.
+struct TomColumnOperand {
+  const void* operand = nullptr;  // planes / cleaned copy of A^T, laid out like the row operand
+  const double* scale = nullptr;  // int8 only
+  const double* k = nullptr;      // column sums of A (NaN for a NaN column when nan_mode)
+  int nan_mode = 0;
+};
+
+int tom_transpose(const double* dA, int64_t n, double* dAt, cudaStream_t st);
+int tom_prepare_impl(const double* dA_rows, int64_t n, int64_t row0, int64_t nrows, int precision, void* d_operand,
+                     int64_t op_rows, double* d_scale, double* d_k, int device, void* stream, int nan_mode);
+int tom_compute_impl(const double* dA_rows, const void* d_operand, int64_t op_rows, const double* d_scale,
+                     const double* d_k, int64_t n, int64_t row0, int64_t nrows, int tom_type, int tom_denom,
+                     int out_mode, int precision, double* d_out, int device, void* stream,
+                     const TomColumnOperand* col);
+
 #ifdef __CUDACC__
 // np.nan_to_num (wgcna.py:1185; default also maps +-inf to +-DBL_MAX, unreachable for a matrix that
 // passed checkAdjMat) and fill_diagonal(A, 0) (wgcna.py:1143)

@@ -33,8 +33,11 @@
 //              finished tiles per row block for a host that copies results out while the kernel runs
 #include <cuda.h>
 
+#include <string.h>
+
 #include <algorithm>
 #include <map>
+#include <mutex>
 #include <vector>
 
 #include "tom_common.cuh"
@@ -59,6 +62,9 @@ struct I8Params {
   const double* A_rows;  // nrows x n original adjacency rows (for a_ij)
   const double* scale;   // op_rows
   const double* k;       // op_rows
+  const double* scale_col;  // scale / k of the column operand (= scale / k unless A is asymmetric,
+  const double* k_col;      //  TomColumnOperand)
+  int32_t nan_mode;         // NaN rows / columns propagate (k = NaN marks them)
   double* out;           // nrows x n
   double* scratch;       // gridDim.x * 128 * 256
   int64_t n, row0, nrows;
@@ -192,17 +198,22 @@ __host__ __device__ constexpr uint32_t make_i8_idesc(int M, int N) {
 __global__ void __launch_bounds__(256)
 tom_prepare_i8_kernel(const double* __restrict__ A_rows, int64_t n, int64_t ldn, int64_t op_rows,
                       int64_t row0, int8_t* __restrict__ planes, double* __restrict__ scale,
-                      double* __restrict__ k) {
+                      double* __restrict__ k, int nan_mode) {
   __shared__ double red[8];
   const int64_t i = row0 + blockIdx.x;
   const double* src = A_rows + (int64_t)blockIdx.x * n;
-  double s = 0.0, mx = 0.0;
+  double s = 0.0, mx = 0.0, nn = 0.0;
   for (int64_t j = threadIdx.x; j < n; j += 256) {
+    if (nan_mode && i != j && isnan(src[j])) nn += 1.0;
     double a = tom_clean(src[j], i, j);
     s += a;
     mx = fmax(mx, fabs(a));
   }
   s = block_sum_256(s);
+  if (nan_mode) {  // no nan_to_num upstream: numpy's plain row sum of a row with a NaN is NaN (wgcna.py:1146)
+    nn = block_sum_256(nn);
+    if (nn > 0.0) s = __longlong_as_double(0x7ff8000000000000LL);
+  }
   for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
   __syncthreads();
@@ -311,7 +322,8 @@ __device__ __forceinline__ void tc_mma_i8_2sm(uint32_t tmem_d, uint64_t adesc, u
 
 template <int kCtas>
 __global__ void __launch_bounds__(kI8Threads, 1)
-tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ I8Params p) {
+tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmapB,
+              const __grid_constant__ I8Params p) {
   using Cfg = I8Cfg<kCtas>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kStageBytes = Cfg::kStageBytes;
@@ -361,6 +373,7 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapB) : "memory");
       int stage = 0;
       uint32_t phase = 0;
       // Every CTA runs the same number of iterations so that the producers can keep in step: CTAs
@@ -416,12 +429,12 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
             if constexpr (kCtas == 1) {
               mbar_expect_tx(&bars->full[stage], kStageBytes);
               tma_load_3d(a_dst, &tmap, &bars->full[stage], kb * kKB, i0, sgm.s);
-              tma_load_3d(b_dst, &tmap, &bars->full[stage], kb * kKB, j0, sgm.t);
-              tma_load_3d(b_dst + 128 * kKB, &tmap, &bars->full[stage], kb * kKB, j0 + 128, sgm.t);
+              tma_load_3d(b_dst, &tmapB, &bars->full[stage], kb * kKB, j0, sgm.t);
+              tma_load_3d(b_dst + 128 * kKB, &tmapB, &bars->full[stage], kb * kKB, j0 + 128, sgm.t);
             } else {
               if (leader) mbar_expect_tx(&bars->full[stage], 2 * kStageBytes);  // both CTAs' bytes
               tma_load_3d_2sm(a_dst, &tmap, &bars->full[stage], kb * kKB, i0, sgm.s);
-              tma_load_3d_2sm(b_dst, &tmap, &bars->full[stage], kb * kKB, j0 + (int)rank * 128, sgm.t);
+              tma_load_3d_2sm(b_dst, &tmapB, &bars->full[stage], kb * kKB, j0 + (int)rank * 128, sgm.t);
             }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
@@ -566,7 +579,7 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
         for (int c = 0; c < kTN / 32; ++c) {
           const int64_t gjl = j0 + c * 32 + lane;
           const int64_t gjc = gjl < p.n ? gjl : p.n - 1;
-          const double sj_l = p.scale[gjc], kj_l = p.k[gjc];  // column values: one per lane, shuffled below
+          const double sj_l = p.scale_col[gjc], kj_l = p.k_col[gjc];  // column values: one per lane, shuffled below
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const double* sc = scratch + ((int64_t)c * 32 + h * 16) * kTM + row;
@@ -585,7 +598,8 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
               const double kj = __shfl_sync(0xffffffffu, kj_l, h * 16 + col);
               const double L = scv[col] * (si * sj);
               const double a = tom_clean(av[col], gi, gj);
-              const double t = tom_value(L, a, ki, kj, gi == gj, p.tom_type, p.tom_denom, p.out_mode);
+              double t = tom_value(L, a, ki, kj, gi == gj, p.tom_type, p.tom_denom, p.out_mode);
+              if (p.nan_mode && gi != gj && (isnan(ki) || isnan(kj))) t = __longlong_as_double(0x7ff8000000000000LL);
               const bool ok = row_ok && gj < p.n;
               if (out_is_condensed(p.out_mode)) {  // entries above the diagonal only, squareform order
                 if (ok && gj > gi) p.out[condensed_index(p.n, gi, gj)] = t;
@@ -653,6 +667,25 @@ static EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
+// true when Nsight Compute's injection libraries are loaded into this process (checked once)
+static bool profiler_attached() {
+  static const bool attached = [] {
+    for (const char* v : {"CUDA_INJECTION64_PATH", "LD_PRELOAD"}) {
+      const char* e = getenv(v);
+      if (e && (strstr(e, "nsight") || strstr(e, "injection") || strstr(e, "Injection"))) return true;
+    }
+    FILE* f = fopen("/proc/self/maps", "r");
+    if (!f) return false;
+    char line[1024];
+    bool hit = false;
+    while (!hit && fgets(line, sizeof line, f))
+      hit = strstr(line, "nsight-compute") || strstr(line, "libcuda-injection") || strstr(line, "TreeLauncher");
+    fclose(f);
+    return hit;
+  }();
+  return attached;
+}
+
 // Digit-pair schedule: pairs (s, t) with s + t >= w_min, grouped by weight (heaviest first), cut into
 // passes of at most kMaxKbPerPass K-blocks.
 static int build_schedule(I8Params& prm, int nkb, int w_min) {
@@ -705,10 +738,10 @@ static int build_schedule(I8Params& prm, int nkb, int w_min) {
 using namespace b200w;
 
 int b200w_tom_prepare_i8(const double* dA_rows, int64_t n, int64_t row0, int64_t nrows, void* d_operand,
-                         int64_t op_rows, double* d_scale, double* d_k, cudaStream_t st) {
+                         int64_t op_rows, double* d_scale, double* d_k, cudaStream_t st, int nan_mode) {
   const int64_t ldn = b200w_padded_n(n);
   tom_prepare_i8_kernel<<<(unsigned)nrows, 256, 0, st>>>(dA_rows, n, ldn, op_rows, row0, (int8_t*)d_operand,
-                                                         d_scale, d_k);
+                                                         d_scale, d_k, nan_mode);
   B200W_LAUNCHED();
   return 0;
 }
@@ -716,7 +749,8 @@ int b200w_tom_prepare_i8(const double* dA_rows, int64_t n, int64_t row0, int64_t
 int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t op_rows, const double* d_scale,
                          const double* d_k, int64_t n, int64_t row0, int64_t nrows, int tom_type, int tom_denom,
                          int out_mode, double* d_out, cudaStream_t st, int world, int rank, int64_t per,
-                         double* const* peer_out, b200w::TomProgress* progress, int w_min_arg) {
+                         double* const* peer_out, b200w::TomProgress* progress, int w_min_arg,
+                         const b200w::TomColumnOperand* col) {
   const int64_t ldn = b200w_padded_n(n);
   if (op_rows > 0x7fffffff || ldn > 0x7fffffff) return fail(B200W_E_UNSUPPORTED, "tom_i8: n too large");
   EncodeTiledFn encode = get_encode_tiled();
@@ -731,11 +765,22 @@ int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t o
                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(B200W_E_CUDA, "tom_i8: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+  CUtensorMap tmapB = tmap;  // asymmetric adjacency: the column operand comes from the planes of A^T
+  if (col != nullptr && col->operand != nullptr && col->operand != d_operand) {
+    cr = encode(&tmapB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(col->operand), gdim, gstride, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(B200W_E_CUDA, "tom_i8: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+  }
+  const bool asym_operand = col != nullptr && col->operand != nullptr && col->operand != d_operand;
 
-  static I8Params prm;  // large (schedule tables); filled per call under the caller's single-thread contract
+  I8Params prm = {};  // per call: entry points may be driven from several host threads / for several devices
   prm.A_rows = dA_rows;
   prm.scale = d_scale;
   prm.k = d_k;
+  prm.scale_col = (col && col->scale) ? col->scale : d_scale;
+  prm.k_col = (col && col->k) ? col->k : d_k;
+  prm.nan_mode = col ? col->nan_mode : 0;
   prm.out = d_out;
   prm.n = n;
   prm.row0 = row0;
@@ -771,13 +816,15 @@ int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t o
   if (world > 8) return fail(B200W_E_UNSUPPORTED, "tom_i8: at most 8 ranks");
   if (dist && (per % 256 != 0 || row0 != rank * per))
     return fail(B200W_E_INVALID, "tom_i8: distributed mode needs per %% 256 == 0 and row0 == rank * per");
-  bool symmetric = (ctas == 2) && ((row0 == 0 && nrows == n) || dist);
+  bool symmetric = (ctas == 2) && ((row0 == 0 && nrows == n) || dist) && !asym_operand;
   if (const char* e = getenv("B200W_I8_SYMMETRIC")) symmetric = symmetric && (atoi(e) != 0 || dist);
   prm.tile_row_base = dist ? 0 : row0;
   prm.per_rows = dist ? per : op_rows;
   for (int r = 0; r < 8; ++r) prm.peer_out[r] = dist && r < world ? peer_out[r] : d_out;
   // the list depends only on (device, TM, TN, G, symmetric, world, rank, per): built once, then cached
   static std::map<std::vector<int>, std::pair<int2*, int>> tile_cache;
+  static std::mutex tile_mu;
+  std::lock_guard<std::mutex> tile_lock(tile_mu);  // (held to the end of the call: launches are asynchronous)
   const std::vector<int> key = {dev, prm.tiles_m, prm.tiles_n, prm.group, symmetric ? 1 : 0,
                                 dist ? world : 1, dist ? rank : 0, dist ? (int)(per / 256) : 0};
   auto hit = tile_cache.find(key);
@@ -845,14 +892,22 @@ int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t o
     if (symmetric && !dist && !out_is_condensed(out_mode)) {
       // expected finalizer-warp arrivals per row block = (warps per tile over the CTA pair) x (tiles that
       // touch the block through their direct rows tm or their mirrored rows tn)
-      static unsigned int* h_flags = nullptr;  // host-mapped, 1024 blocks
-      static unsigned int *d_flags = nullptr, *d_counts = nullptr, *d_expected = nullptr;
-      if (!h_flags) {
-        B200W_CUDA(cudaHostAlloc((void**)&h_flags, 1024 * sizeof(unsigned int), cudaHostAllocMapped));
-        B200W_CUDA(cudaHostGetDevicePointer((void**)&d_flags, h_flags, 0));
-        B200W_CUDA(cudaMalloc(&d_counts, 1024 * sizeof(unsigned int)));
-        B200W_CUDA(cudaMalloc(&d_expected, 1024 * sizeof(unsigned int)));
+      // one set per (host thread, device): a second device in the same process must not get device-0
+      // pointers, and two host threads must not share counters
+      struct ProgBufs {
+        unsigned int* h_flags = nullptr;  // host-mapped, 1024 blocks
+        unsigned int *d_flags = nullptr, *d_counts = nullptr, *d_expected = nullptr;
+      };
+      static thread_local std::map<int, ProgBufs> prog_bufs;
+      ProgBufs& pb = prog_bufs[dev];
+      if (!pb.h_flags) {
+        B200W_CUDA(cudaHostAlloc((void**)&pb.h_flags, 1024 * sizeof(unsigned int), cudaHostAllocMapped));
+        B200W_CUDA(cudaHostGetDevicePointer((void**)&pb.d_flags, pb.h_flags, 0));
+        B200W_CUDA(cudaMalloc(&pb.d_counts, 1024 * sizeof(unsigned int)));
+        B200W_CUDA(cudaMalloc(&pb.d_expected, 1024 * sizeof(unsigned int)));
       }
+      unsigned int* const h_flags = pb.h_flags;
+      unsigned int *const d_flags = pb.d_flags, *const d_counts = pb.d_counts, *const d_expected = pb.d_expected;
       const int Gp = prm.prog_tiles, nb = (prm.tiles_m + Gp - 1) / Gp;
       if (nb <= 1024) {
         std::vector<unsigned int> expect(nb, 0u);
@@ -899,9 +954,10 @@ int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t o
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     int na = 0;
-    // (B200W_I8_NOCOOP=1 drops the attribute: Nsight Compute 2025.2 fails to replay a launch that is
-    //  both cooperative and clustered; the grid is one CTA per SM, so it is co-resident in practice)
-    if (!getenv("B200W_I8_NOCOOP")) {
+    // (Nsight Compute 2025.2 fails to replay a launch that is both cooperative and clustered, so the
+    //  attribute is dropped when its injection libraries are mapped into the process -- or with
+    //  B200W_I8_NOCOOP=1; the grid is one CTA per SM, so it is co-resident in practice)
+    if (!getenv("B200W_I8_NOCOOP") && !profiler_attached()) {
       attr[na].id = cudaLaunchAttributeCooperative;
       attr[na].val.cooperative = 1;
       ++na;
@@ -915,7 +971,7 @@ int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t o
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tmap, prm);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, tmap, tmapB, prm);
     if (le != cudaSuccess) {
       return fail(B200W_E_CUDA, "tom_i8: launch failed (%s), grid %d x %d threads, %d-CTA groups, %zu B smem",
                   cudaGetErrorString(le), grid, kI8Threads, ctas, smem);

@@ -267,11 +267,11 @@ class DeviceNetwork:
     def tom_compute(self, TOMType: str = "signed", TOMDenom: str = "min", out_mode: int = L.OUT_TOM):
         tt, td = L.TOM_TYPES.index(TOMType), L.TOM_DENOMS.index(TOMDenom)
         T = self._out()
+        if self.fused and self._peer_ptrs is None:
+            self.connect_peers()  # a collective: every rank takes part, also one without rows
         if self.nrows == 0:
             return T[:0]
         if self.fused:
-            if self._peer_ptrs is None:
-                self.connect_peers()
             L.check(self.lib.b200w_dev_tom_compute_dist(self._A_rows.data_ptr(), self._op.data_ptr(), self.op_rows,
                                                         self._scale.data_ptr(), self._k.data_ptr(), self.n,
                                                         self.world, self.rank, self.per, tt, td, out_mode,
@@ -301,3 +301,50 @@ class DeviceNetwork:
         T = self.tom_compute(TOMType, TOMDenom, out_mode)
         self.tom_finish()
         return T
+
+
+def network_blocks(datExpr, powerVector=None, networkType="unsigned", TOMType="signed", TOMDenom="min",
+                   RsquaredCut=0.9, MeanCut=100, nBreaks=10, power=None, device=None, precision="auto",
+                   out_mode: int = L.OUT_TOM, return_adjacency: bool = False):
+    """Sharded host entry point: host expression matrix in, host results
+    out, everything in between resident on this process's GPU.  The chain is the one ``findModules`` runs
+    (wgcna.py:278 -> :310 -> :320): ``pickSoftThreshold`` (skipped when ``power`` is given), ``adjacency``
+    at the selected power, ``TOMsimilarity``.
+
+    Under torchrun (an initialised process group) every rank passes the same ``datExpr`` and gets back the
+    rows ``[row0, row0 + nrows)`` it owns; per rank the PCIe traffic is the m x n expression matrix up and
+    its n^2 / G block down, instead of the three n^2 transfers of the reference-shaped calls.
+
+    Returns a dict: ``power``, ``sft`` (the P x 7 table, or None), ``rows`` = (row0, nrows), ``TOM``
+    (nrows x n ndarray in a page-locked buffer; ``1 - TOM`` etc. per ``out_mode``) and, on request,
+    ``adjacency`` (nrows x n)."""
+    import pandas as pd
+
+    X = L.as_f64_matrix(datExpr)
+    lib = L.load()
+    dev = L.default_device() if device is None else int(device)
+    torch.cuda.set_device(dev)
+    m, n = X.shape
+    Xd = torch.empty((m, n), dtype=torch.float64, device=torch.device("cuda", dev))
+    st = torch.cuda.current_stream(Xd.device).cuda_stream
+    L.check(lib.b200w_dev_upload(Xd.data_ptr(), L.hptr(X), X.nbytes, dev, st))
+    net = DeviceNetwork(Xd, device=dev, networkType=networkType, precision=precision)
+    sft = None
+    if power is None:
+        pv = np.sort(np.asarray(list(range(1, 11)) + list(range(1, 21, 2)) if powerVector is None else powerVector))
+        power, cols = net.sft(pv, nBreaks=nBreaks, RsquaredCut=RsquaredCut, MeanCut=MeanCut)
+        names = ["Power", "SFT.R.sq", "slope", "truncated R.sq", "mean(k)", "median(k)", "max(k)"]
+        sft = pd.DataFrame({"Power": pv, **{c: cols[c] for c in names[1:]}}, columns=names).astype(object)
+    A = net.adjacency(float(power))
+    res = {"power": power, "sft": sft, "rows": (net.row0, net.nrows)}
+    if return_adjacency:
+        a_host = L.result_empty((net.nrows, n))
+        if net.nrows:
+            L.check(lib.b200w_dev_download(L.hptr(a_host), A.data_ptr(), a_host.nbytes, dev, st))
+        res["adjacency"] = a_host
+    T = net.tom(TOMType=TOMType, TOMDenom=TOMDenom, out_mode=out_mode)
+    t_host = L.result_empty((net.nrows, n))
+    if net.nrows:
+        L.check(lib.b200w_dev_download(L.hptr(t_host), T.data_ptr(), t_host.nbytes, dev, st))
+    res["TOM"] = t_host
+    return res

@@ -425,7 +425,7 @@ def checkAdjMat(adjMat, min=0, max=1, device=None):
         adjMat = adjMat.to_numpy()
     _check_shape_dtype(adjMat)
     A = np.ascontiguousarray(adjMat, dtype=np.float64)
-    stats = np.empty(4, dtype=np.float64)
+    stats = np.empty(6, dtype=np.float64)
     L.check(L.load().b200w_check_adjacency(L.hptr(A), A.shape[0], L.hptr(stats), _device(device)))
     if stats[3] > 0:  # a NaN makes np.max / np.min NaN: both comparisons of the reference are False
         return
@@ -449,7 +449,7 @@ def checkSimilarity(adjMat, min=-1, max=1, device=None):
     if dim[0] != dim[1]:
         sys.exit("adjacency is not square")
     A = np.ascontiguousarray(adjMat, dtype=np.float64)
-    stats = np.empty(4, dtype=np.float64)
+    stats = np.empty(6, dtype=np.float64)
     L.check(L.load().b200w_check_adjacency(L.hptr(A), A.shape[0], L.hptr(stats), _device(device)))
     if stats[3] > 0:
         return
@@ -479,15 +479,18 @@ def _tom(adjMat, TOMTypeC, TOMDenomC, check, out_mode=L.OUT_TOM, device=None, ro
     # the reference works in place on its argument (NaN -> 0 :1185, diagonal -> 0 :1143); mirror the
     # visible side effect when the caller's buffer is writable (pandas < 3 hands findModules a view)
     if isinstance(adjMat, np.ndarray) and adjMat.flags.writeable and adjMat.dtype == np.float64:
-        if not check or stats[3] > 0:
-            np.nan_to_num(adjMat, copy=False, nan=0)
+        if check and stats[3] > 0:
+            np.nan_to_num(adjMat, copy=False, nan=0)  # TOMsimilarity only (:1185)
         np.fill_diagonal(adjMat, 0)
     return out
 
 
 def TomSimilarityFromAdj(adjMat, TOMDenom, TOMType, device=None):
-    """``WGCNA.TomSimilarityFromAdj`` (wgcna.py:1141-1157): integer codes in, ndarray out, no checks.
-    (Unlike ``TOMsimilarity`` the reference does not zero NaNs here; a NaN input is zeroed anyway.)"""
+    """``WGCNA.TomSimilarityFromAdj`` (wgcna.py:1141-1157): integer codes in, ndarray out, no checks and
+    no ``nan_to_num``.  As in the reference, a NaN makes every entry of its row and of its column NaN
+    (numpy's ``A @ A`` and plain sums; the diagonal is still set to 1), and a matrix that is not symmetric
+    is contracted as ``A @ A`` with the column sums ``k_j`` (the library then takes its column operand
+    from ``A^T`` instead of mirroring tiles)."""
     return _tom(adjMat, int(TOMType), int(TOMDenom), check=False, device=device)
 
 
@@ -537,6 +540,14 @@ def network(datExpr, power=6, networkType="unsigned", TOMType="signed", TOMDenom
     L.check(L.load().b200w_network(L.hptr(X), m, n, intType, float(power), TOMTypeC, TOMDenomC, L.OUT_TOM, prec,
                                    L.hptr(A) if A is not None else None, L.hptr(T), _device(device)))
     return A, pd.DataFrame(T, copy=False)
+
+
+def network_blocks(datExpr, *args, **kwargs):
+    """Sharded host entry point: expression matrix in, this rank's row block of the TOM out (one process per
+    GPU under torchrun); see ``pywgcna_b200.device.network_blocks``.  (Imported lazily: it needs torch.)"""
+    from .device import network_blocks as impl
+
+    return impl(datExpr, *args, **kwargs)
 
 
 # ----------------------------------------------------------------------------------------------

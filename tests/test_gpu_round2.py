@@ -1,0 +1,127 @@
+"""GPU parity tests added in round 2 (all through the C ABI, against goldens of the unmodified reference or
+the restated oracle): TomSimilarityFromAdj on unchecked input, full-size C2 soft-threshold table, several
+devices driven from one process."""
+import os
+import threading
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import pywgcna_b200 as bw
+from oracle import restated as O
+from pywgcna_b200 import _lib
+from pywgcna_b200.synth import CONFIGS, make_expression
+
+pytestmark = pytest.mark.gpu
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+# ------------------------------------------------------------------------------------------------
+# TomSimilarityFromAdj, wgcna.py:1141-1157: no checks and no nan_to_num
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec", ["f64", "i8"])
+@pytest.mark.parametrize("nm", ["asym", "sym_nan", "asym_nan", "signed_asym"])
+def test_tom_from_adj_unchecked(gpu, golden_dir, nm, prec, monkeypatch):
+    """Public name, reference goldens: an asymmetric matrix is contracted as A @ A with column sums k_j,
+    a NaN makes its whole row and column NaN (diagonal 1); tolerance 1e-10 (north-star: 1e-6)."""
+    monkeypatch.setattr(bw.wgcna, "PRECISION", prec)
+    g = load(golden_dir, "tom_from_adj")
+    for tt, td in ((0, 0), (1, 1)):
+        A = g[f"A_{nm}"].copy()
+        T = bw.TomSimilarityFromAdj(A, td, tt)
+        ref = g[f"fromadj_{nm}_{tt}_{td}"]
+        assert np.array_equal(np.isnan(T), np.isnan(ref))
+        np.testing.assert_allclose(T, ref, rtol=0, atol=1e-10, equal_nan=True)
+        # the in-place side effect of the reference: diagonal zeroed (:1143), NaNs left alone
+        assert np.all(np.diag(A) == 0)
+        assert np.isnan(A).sum() == np.isnan(g[f"A_{nm}"]).sum() - np.isnan(np.diag(g[f"A_{nm}"])).sum()
+
+
+@pytest.mark.parametrize("prec", ["f64", "i8"])
+@pytest.mark.parametrize("nm", ["sym_nan", "asym_nan"])
+def test_tomsimilarity_on_matrix_waved_through_by_nan(gpu, golden_dir, nm, prec):
+    """TOMsimilarity: a NaN makes both comparisons of checkAdjMat False (wgcna.py:1135-1138), so even an
+    asymmetric matrix reaches nan_to_num (:1185) and the contraction."""
+    g = load(golden_dir, "tom_from_adj")
+    for tt in ("unsigned", "signed"):
+        A = g[f"A_{nm}"].copy()
+        T = bw.TOMsimilarity(A, TOMType=tt, precision=prec).to_numpy()
+        np.testing.assert_allclose(T, g[f"tomsim_{nm}_{tt}"], rtol=0, atol=1e-10)
+        assert not np.isnan(A).any() and np.all(np.diag(A) == 0)  # :1185 and :1143, in place
+
+
+def test_tom_from_adj_symmetric_matches_tomsimilarity(gpu):
+    """For a clean symmetric adjacency the unchecked and the checked entry give the same bits."""
+    X = make_expression(40, 517, F=4, seed=11)
+    A = bw.adjacency(pd.DataFrame(X), adjacencyType="signed hybrid", power=6)
+    T0 = bw.TOMsimilarity(A.copy(), TOMType="signed").to_numpy()
+    T1 = bw.TomSimilarityFromAdj(A.copy(), 0, 1)
+    assert np.array_equal(T0, T1)
+
+
+# ------------------------------------------------------------------------------------------------
+# full-size C2: the reference's own soft-threshold table and selected power (wgcna.py:924-953)
+# ------------------------------------------------------------------------------------------------
+def test_c2_fullsize_soft_threshold_table(gpu, golden_dir):
+    """20 000 x 200, signed hybrid, powers 1..20: identical selected power, and every column of the 20 x 7
+    table of the unmodified reference (tests/golden/c2_fullsize.npz, oracle/gen_golden_large.py)."""
+    g = load(golden_dir, "c2_fullsize")
+    m, n, F, seed, net, tom = CONFIGS["C2"]
+    X = make_expression(m, n, F=F, seed=seed)
+    df = pd.DataFrame(X)
+    p, sft = bw.pickSoftThreshold(df, networkType=net, powerVector=list(g["powers"]))
+    assert int(p) == int(g["power"])
+    got, ref = sft.to_numpy(dtype=float), g["sft"]
+    assert np.array_equal(got[:, 0], ref[:, 0])
+    np.testing.assert_allclose(got[:, 1:4], ref[:, 1:4], rtol=0, atol=1e-9)   # R^2, slope, truncated R^2
+    np.testing.assert_allclose(got[:, 4:], ref[:, 4:], rtol=1e-12, atol=0)    # mean, median, max of k
+    # sampled rows of the reference's adjacency and TOM at that power
+    rows = g["rows"]
+    A = bw.adjacency(df, adjacencyType=net, power=p)
+    np.testing.assert_allclose(A[rows], g["adj_rows"], rtol=0, atol=1e-12)
+    T = bw.TOMsimilarity(A, TOMType=tom).to_numpy()
+    np.testing.assert_allclose(T[rows], g["tom_rows"], rtol=0, atol=1e-10)
+
+
+# ------------------------------------------------------------------------------------------------
+# one host process, several devices / several host threads (SURVEY 8b threading contract)
+# ------------------------------------------------------------------------------------------------
+def test_two_host_threads_one_device(gpu):
+    """Two Python threads inside b200w_tom at once (ctypes releases the GIL): per-call parameters and
+    per-thread progress buffers, same bits as the serial calls."""
+    X = make_expression(50, 2304, F=5, seed=21)
+    A = bw.adjacency(pd.DataFrame(X), adjacencyType="unsigned", power=4)
+    ref = bw.TOMsimilarity(A.copy(), TOMType="unsigned").to_numpy().copy()
+    out, err = [None, None], []
+
+    def work(i):
+        try:
+            for _ in range(3):
+                out[i] = bw.TOMsimilarity(A.copy(), TOMType="unsigned").to_numpy().copy()
+        except Exception as e:  # pragma: no cover
+            err.append(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not err, err
+    assert np.array_equal(out[0], ref) and np.array_equal(out[1], ref)
+
+
+def test_second_device_same_process(gpu):
+    """b200w_tom on device 0 and then device 1 from one process (progress flags, tile lists and caches are
+    keyed by device).  Skipped on a one-GPU box."""
+    if _lib.device_count() < 2:
+        pytest.skip("needs two visible GPUs")
+    X = make_expression(50, 2304, F=5, seed=22)
+    A = bw.adjacency(pd.DataFrame(X), adjacencyType="unsigned", power=4, device=0)
+    T0 = bw.TOMsimilarity(A.copy(), TOMType="unsigned", device=0).to_numpy().copy()
+    T1 = bw.TOMsimilarity(A.copy(), TOMType="unsigned", device=1).to_numpy().copy()
+    T0b = bw.TOMsimilarity(A.copy(), TOMType="unsigned", device=0).to_numpy().copy()
+    assert np.array_equal(T0, T1) and np.array_equal(T0, T0b)
+    ref = O.TOMsimilarity(A.copy(), TOMType="unsigned").to_numpy()
+    np.testing.assert_allclose(T1, ref, rtol=0, atol=1e-10)

@@ -166,6 +166,7 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "TFLOP/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["full_workload"] is True and line["steps"] == 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["config"]["workload"].startswith("tiny") or "tiny" in json.dumps(line["config"])
