@@ -432,7 +432,7 @@ def measure_ours(args, wl, steps, warmup, world, rank, local, with_e2e, with_fas
     phases = {"soft_threshold": float(np.mean([a.elapsed_time(b) for a, b, _, _ in phase_events])),
               "adjacency": float(np.mean([b.elapsed_time(c) for _, b, c, _ in phase_events])),
               "tom": float(np.mean([c.elapsed_time(d) for _, _, c, d in phase_events]))}
-    power = int(state["power"]) if not hasattr(state["power"], "item") else int(state["power"].item())
+    power = int(state["power"].item()) if hasattr(state["power"], "item") else int(state["power"])
 
     # hardware parity of the path that was just timed (every rank, real NCCL / IPC path at N > 1)
     parity = tom_parity_probe(net_dev, state["T"], tom_type)

@@ -192,6 +192,20 @@ int b200w_dev_sft_stats(const double* d_k, int P, int64_t n, int64_t ldk, int nb
 int b200w_dev_adjacency(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t n, int net_type,
                         double power, int64_t row0, int64_t nrows, double* dA, int device,
                         void* stream);
+/* The statistics above plus, still on the device, what WGCNA.pickSoftThreshold decides from them
+ * (wgcna.py:924-953): d_fit[p] = (R^2 of the first ten-point regression of scaleFreeFitIndex :1039, exactly
+ * rounded statistics.mean :930), and d_power_out[0] = the selected power = the smallest of d_powers[P]
+ * (ascending, device memory) with R^2 > rsq_cut and mean(k) <= mean_cut, else the power of the largest R^2
+ * (:945-953); d_power_out[1] = its index.  Nothing is copied to the host: the *_dp entry points below read
+ * the power from device memory, so a chained step never waits for the host. */
+int b200w_dev_sft_select(const double* d_k, int P, int64_t n, int64_t ldk, int nbreaks, const double* d_powers,
+                         double rsq_cut, double mean_cut, double* d_stats, int64_t* d_buckets,
+                         double* d_fit /* P x 2 */, double* d_power_out /* 2 */, int device, void* stream);
+int b200w_dev_adjacency_dp(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t n, int net_type,
+                           const double* d_power, int64_t row0, int64_t nrows, double* dA, int device,
+                           void* stream);
+int b200w_dev_adjacency_from_similarity_dp(double* d_sim_inout, int64_t nrows, int64_t n, const double* d_power,
+                                           int device, void* stream);
 int b200w_dev_check_adjacency(const double* dA, int64_t n, double* d_stats6, int device,
                               void* stream);
 
@@ -234,6 +248,27 @@ int b200w_dev_tom_compute_dist(const double* dA_rows, const void* d_operand, int
                                int64_t per, int tom_type, int tom_denom, int out_mode,
                                void* const* peer_out /* host array of `world` device pointers */,
                                int device, void* stream);
+
+/* The same contraction with its operand exchange overlapped (multi-GPU).  Instead of all-gathering the digit
+ * planes before the kernel starts, every rank keeps planes, scale and k in ONE shareable allocation
+ * (b200w_dev_malloc of b200w_tom_shared_bytes(op_rows, n): planes at 0, scale at
+ * b200w_tom_shared_scale_offset, k right behind it; d_operand / d_scale / d_k of the calls above point into
+ * it) and, once all ranks have prepared their rows, calls b200w_dev_tom_pull_planes on a COPY stream: the
+ * peers' rows of scale and k, then plane 4, 3, ... 0 are copied out of the peers' HBM by the copy engines
+ * (peer_base[q] = rank q's allocation, peer-mapped), and after each plane d_plane_flags[s] is set to `epoch`
+ * by a stream memory operation.  b200w_dev_tom_compute_dist_gated, launched at once on the compute stream,
+ * starts with the pairs of the heaviest plane and waits at the first use of each further plane until its
+ * flag has reached `epoch` (a wrapping 32-bit counter, incremented by the caller per exchange). */
+int64_t b200w_tom_shared_scale_offset(int64_t op_rows, int64_t n);
+int64_t b200w_tom_shared_bytes(int64_t op_rows, int64_t n);
+int b200w_dev_tom_pull_planes(void* d_local, void* const* peer_base, int world, int rank, int64_t per,
+                              int64_t op_rows, int64_t n, uint32_t* d_plane_flags /* B200W_I8_SLICES */,
+                              uint32_t epoch, int device, void* copy_stream);
+int b200w_dev_tom_compute_dist_gated(const double* dA_rows, const void* d_operand, int64_t op_rows,
+                                     const double* d_scale, const double* d_k, int64_t n, int world, int rank,
+                                     int64_t per, int tom_type, int tom_denom, int out_mode,
+                                     void* const* peer_out, const uint32_t* d_plane_flags, uint32_t plane_epoch,
+                                     int device, void* stream);
 
 /* Device buffers that can be shared between the per-GPU processes of one node (plain cudaMalloc, hence
  * exportable), and the CUDA IPC plumbing for them.  handle = 64 bytes (cudaIpcMemHandle_t). */

@@ -61,6 +61,9 @@ SIGNATURES = {
     "b200w_dev_sweep": (_int, [_dp, _dp, _i64, _i64, _dp, _int, _int, _i64, _i64, _dp, _int, _dp]),
     "b200w_dev_sweep_similarity": (_int, [_dp, _dp, _i64, _i64, _dp, _int, _int, _i64, _i64, _dp, _dp, _int, _dp]),
     "b200w_dev_adjacency_from_similarity": (_int, [_dp, _i64, _i64, _dbl, _int, _dp]),
+    "b200w_dev_adjacency_from_similarity_dp": (_int, [_dp, _i64, _i64, _dp, _int, _dp]),
+    "b200w_dev_adjacency_dp": (_int, [_dp, _dp, _i64, _i64, _int, _dp, _i64, _i64, _dp, _int, _dp]),
+    "b200w_dev_sft_select": (_int, [_dp, _int, _i64, _i64, _int, _dp, _dbl, _dbl, _dp, _dp, _dp, _dp, _int, _dp]),
     "b200w_dev_adjacency": (_int, [_dp, _dp, _i64, _i64, _int, _dbl, _i64, _i64, _dp, _int, _dp]),
     "b200w_dev_check_adjacency": (_int, [_dp, _i64, _dp, _int, _dp]),
     "b200w_padded_n": (_i64, [_i64]),
@@ -70,6 +73,12 @@ SIGNATURES = {
                                      _dp, _int, _dp]),
     "b200w_dev_tom_compute_dist": (_int, [_dp, _dp, _i64, _dp, _dp, _i64, _int, _int, _i64, _int, _int, _int,
                                           C.POINTER(C.c_void_p), _int, _dp]),
+    "b200w_tom_shared_scale_offset": (_i64, [_i64, _i64]),
+    "b200w_tom_shared_bytes": (_i64, [_i64, _i64]),
+    "b200w_dev_tom_pull_planes": (_int, [_dp, C.POINTER(C.c_void_p), _int, _int, _i64, _i64, _i64, _dp, C.c_uint32,
+                                         _int, _dp]),
+    "b200w_dev_tom_compute_dist_gated": (_int, [_dp, _dp, _i64, _dp, _dp, _i64, _int, _int, _i64, _int, _int, _int,
+                                                C.POINTER(C.c_void_p), _dp, C.c_uint32, _int, _dp]),
     "b200w_dev_malloc": (_int, [_i64, _int, C.POINTER(C.c_void_p)]),
     "b200w_dev_free": (_int, [_dp, _int]),
     "b200w_ipc_export": (_int, [_dp, C.c_char_p]),

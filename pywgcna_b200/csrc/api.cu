@@ -18,7 +18,8 @@ int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t o
                          const double* d_k, int64_t n, int64_t row0, int64_t nrows, int tom_type, int tom_denom,
                          int out_mode, double* d_out, cudaStream_t st, int world, int rank, int64_t per,
                          double* const* peer_out, b200w::TomProgress* progress, int w_min,
-                         const b200w::TomColumnOperand* col);
+                         const b200w::TomColumnOperand* col, const unsigned int* d_plane_flags = nullptr,
+                         unsigned int plane_epoch = 0);
 
 namespace b200w {
 

@@ -430,6 +430,11 @@ constexpr int kAdjStages = 3;   // narrow-engine ring slots of the adjacency (tw
 constexpr int kCrossStages = 4;  // wide-engine ring slots of the cross-correlation
 constexpr int kAdjPitch = 33;    // odd: the transposed (mirror) reads of the parked tile stay 2-way at worst
 
+// integer powers up to 64 are evaluated by repeated squaring (0: use pow())
+__host__ __device__ __forceinline__ int small_int_power(double power) {
+  return (power == (double)(int)power && power >= 1.0 && power <= 64.0) ? (int)power : 0;
+}
+
 // s ** e by binary exponentiation for four values at once (same multiplication order for every value, so
 // a symmetric pair of correlations gives bitwise equal adjacencies)
 __device__ __forceinline__ void int_pow4(double (&s)[4], int e) {
@@ -452,9 +457,13 @@ __device__ __forceinline__ void int_pow4(double (&s)[4], int e) {
 // tiles_n counts 128-wide column tiles; a CTA takes the left or right 64 columns of one tile.
 __global__ void __launch_bounds__(kNarrowThreads, 2)
 adjacency_kernel(const double* __restrict__ Z, const uint8_t* __restrict__ bad, int64_t n,
-                 int64_t ldk, int net_type, double power, int ipower, int64_t row0, int64_t nrows,
-                 int symmetric, int64_t tiles_n, double* __restrict__ A) {
+                 int64_t ldk, int net_type, double power, int ipower, const double* __restrict__ d_power,
+                 int64_t row0, int64_t nrows, int symmetric, int64_t tiles_n, double* __restrict__ A) {
   constexpr int kBN = kNarrowBN, kParts = 128 / kBN;
+  if (d_power != nullptr) {  // the power the device-side selection left in HBM (no host round trip)
+    power = *d_power;
+    ipower = small_int_power(power);
+  }
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wm = warp >> 1, wn = warp & 1;
@@ -539,7 +548,12 @@ adjacency_kernel(const double* __restrict__ Z, const uint8_t* __restrict__ bad, 
 // same multiplication order as adjacency_kernel, so both routes give bitwise equal matrices.  HBM bound:
 // 16 bytes per element.
 __global__ void __launch_bounds__(256)
-similarity_power_kernel(double* __restrict__ A, int64_t total, double power, int ipower) {
+similarity_power_kernel(double* __restrict__ A, int64_t total, double power, int ipower,
+                        const double* __restrict__ d_power) {
+  if (d_power != nullptr) {
+    power = *d_power;
+    ipower = small_int_power(power);
+  }
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
   for (int64_t e0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; e0 < total; e0 += stride) {
@@ -663,18 +677,34 @@ extern "C" int b200w_dev_sweep_similarity(const double* dZ, const uint8_t* d_bad
   return sweep_impl(dZ, d_bad, m, n, h_steps, P, net_type, col0, ncols, d_k, d_sim, device, stream);
 }
 
+static int adjacency_from_similarity_impl(double* d_sim_inout, int64_t nrows, int64_t n, double power,
+                                          const double* d_power, int device, void* stream);
+
 extern "C" int b200w_dev_adjacency_from_similarity(double* d_sim_inout, int64_t nrows, int64_t n, double power,
                                                    int device, void* stream) {
-  if (!d_sim_inout || n < 1 || nrows < 1 || nrows > n || !(power > 0.0))
+  if (!(power > 0.0)) return fail(B200W_E_INVALID, "adjacency_from_similarity: bad args");
+  return adjacency_from_similarity_impl(d_sim_inout, nrows, n, power, nullptr, device, stream);
+}
+
+extern "C" int b200w_dev_adjacency_from_similarity_dp(double* d_sim_inout, int64_t nrows, int64_t n,
+                                                      const double* d_power, int device, void* stream) {
+  if (!d_power) return fail(B200W_E_INVALID, "adjacency_from_similarity_dp: bad args");
+  return adjacency_from_similarity_impl(d_sim_inout, nrows, n, 1.0, d_power, device, stream);
+}
+
+static int adjacency_from_similarity_impl(double* d_sim_inout, int64_t nrows, int64_t n, double power,
+                                          const double* d_power, int device, void* stream) {
+  if (!d_sim_inout || n < 1 || nrows < 1 || nrows > n)
     return fail(B200W_E_INVALID, "adjacency_from_similarity: bad args");
   if (int e = ensure_device(device)) return e;
   int sms = 0;
   B200W_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-  const int ipower = (power == (double)(int)power && power >= 1.0 && power <= 64.0) ? (int)power : 0;
+  const int ipower = small_int_power(power);
   const int64_t total = nrows * n, per_block = 256 * 4;
   int64_t blocks = (total + per_block - 1) / per_block;
   if (blocks > (int64_t)sms * 16) blocks = (int64_t)sms * 16;
-  similarity_power_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_sim_inout, total, power, ipower);
+  similarity_power_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_sim_inout, total, power, ipower,
+                                                                              d_power);
   B200W_LAUNCHED();
   return 0;
 }
@@ -763,9 +793,24 @@ static int sweep_impl(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t
   return 0;
 }
 
+static int adjacency_impl(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t n, int net_type, double power,
+                          const double* d_power, int64_t row0, int64_t nrows, double* dA, int device, void* stream);
+
 extern "C" int b200w_dev_adjacency(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t n,
                                    int net_type, double power, int64_t row0, int64_t nrows,
                                    double* dA, int device, void* stream) {
+  return adjacency_impl(dZ, d_bad, m, n, net_type, power, nullptr, row0, nrows, dA, device, stream);
+}
+
+extern "C" int b200w_dev_adjacency_dp(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t n,
+                                      int net_type, const double* d_power, int64_t row0, int64_t nrows,
+                                      double* dA, int device, void* stream) {
+  if (!d_power) return fail(B200W_E_INVALID, "adjacency_dp: bad args");
+  return adjacency_impl(dZ, d_bad, m, n, net_type, 1.0, d_power, row0, nrows, dA, device, stream);
+}
+
+static int adjacency_impl(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t n, int net_type, double power,
+                          const double* d_power, int64_t row0, int64_t nrows, double* dA, int device, void* stream) {
   if (!dZ || !d_bad || !dA || n < 1 || row0 < 0 || nrows < 1 || row0 + nrows > n)
     return fail(B200W_E_INVALID, "adjacency: bad args");
   if (net_type < 0 || net_type > 2) return fail(B200W_E_INVALID, "adjacency: bad network type");
@@ -774,14 +819,14 @@ extern "C" int b200w_dev_adjacency(const double* dZ, const uint8_t* d_bad, int64
   const size_t smem = Narrow::smem_bytes(kAdjStages);
   B200W_CUDA(cudaFuncSetAttribute(adjacency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
-  int ipower = (power == (double)(int)power && power >= 1.0 && power <= 64.0) ? (int)power : 0;
+  int ipower = small_int_power(power);
   const int64_t row_tiles = (nrows + kBM - 1) / kBM, col_tiles = (n + 127) / 128;
   const int symmetric = (row0 == 0 && nrows == n) ? 1 : 0;
   const int64_t blocks = 2 * (symmetric ? col_tiles * (col_tiles + 1) / 2 : row_tiles * col_tiles);
   if (blocks > 2147483647LL) return fail(B200W_E_UNSUPPORTED, "adjacency: too many tiles");
   adjacency_kernel<<<(unsigned)blocks, kNarrowThreads, smem, st>>>(dZ, d_bad, n, b200w_padded_k(m),
-                                                                  net_type, power, ipower, row0, nrows,
-                                                                  symmetric, col_tiles, dA);
+                                                                  net_type, power, ipower, d_power, row0,
+                                                                  nrows, symmetric, col_tiles, dA);
   B200W_LAUNCHED();
   return 0;
 }

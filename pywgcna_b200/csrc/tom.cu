@@ -2,6 +2,8 @@
 // the FP64 (DMMA) contraction + TOM epilogue, intramodular connectivity.
 // Reference: PyWGCNA/wgcna.py:1114-1138 (checkAdjMat), :1141-1157 (TomSimilarityFromAdj),
 // :1160-1193 (TOMsimilarity), :3403-3450 (intramodularConnectivity).
+#include <cuda.h>
+
 #include "gemm_f64.cuh"
 #include "tom_common.cuh"
 
@@ -244,7 +246,8 @@ int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t o
                          const double* d_k, int64_t n, int64_t row0, int64_t nrows, int tom_type,
                          int tom_denom, int out_mode, double* d_out, cudaStream_t st, int world,
                          int rank, int64_t per, double* const* peer_out, b200w::TomProgress* progress,
-                         int w_min, const b200w::TomColumnOperand* col);
+                         int w_min, const b200w::TomColumnOperand* col, const unsigned int* d_plane_flags = nullptr,
+                         unsigned int plane_epoch = 0);
 
 int b200w::resolve_precision(int precision) {
   if (precision == B200W_PREC_AUTO) return B200W_PREC_I8;
@@ -336,11 +339,11 @@ int b200w::tom_compute_impl(const double* dA_rows, const void* d_operand, int64_
   return fail(B200W_E_INVALID, "tom_compute: unknown precision %d", precision);
 }
 
-extern "C" int b200w_dev_tom_compute_dist(const double* dA_rows, const void* d_operand,
-                                          int64_t op_rows, const double* d_scale, const double* d_k,
-                                          int64_t n, int world, int rank, int64_t per, int tom_type,
-                                          int tom_denom, int out_mode, void* const* peer_out,
-                                          int device, void* stream) {
+static int tom_compute_dist_impl(const double* dA_rows, const void* d_operand, int64_t op_rows,
+                                 const double* d_scale, const double* d_k, int64_t n, int world, int rank,
+                                 int64_t per, int tom_type, int tom_denom, int out_mode, void* const* peer_out,
+                                 const unsigned int* d_plane_flags, unsigned int plane_epoch, int device,
+                                 void* stream) {
   if (!dA_rows || !d_operand || !d_scale || !d_k || !peer_out || n < 1 || world < 1 || world > 8 ||
       rank < 0 || rank >= world || per < 256 || per % 256)
     return fail(B200W_E_INVALID, "tom_compute_dist: bad args");
@@ -356,7 +359,81 @@ extern "C" int b200w_dev_tom_compute_dist(const double* dA_rows, const void* d_o
     if (!peer_out[r] && (int64_t)r * per < n) return fail(B200W_E_INVALID, "tom_compute_dist: peer_out[%d] is NULL", r);
   return b200w_tom_compute_i8(dA_rows, d_operand, op_rows, d_scale, d_k, n, row0, nrows, tom_type,
                               tom_denom, out_mode, (double*)peer_out[rank], (cudaStream_t)stream, world,
-                              rank, per, (double* const*)peer_out, nullptr, prec_w_min(B200W_PREC_I8), nullptr);
+                              rank, per, (double* const*)peer_out, nullptr, prec_w_min(B200W_PREC_I8), nullptr,
+                              d_plane_flags, plane_epoch);
+}
+
+extern "C" int b200w_dev_tom_compute_dist(const double* dA_rows, const void* d_operand,
+                                          int64_t op_rows, const double* d_scale, const double* d_k,
+                                          int64_t n, int world, int rank, int64_t per, int tom_type,
+                                          int tom_denom, int out_mode, void* const* peer_out,
+                                          int device, void* stream) {
+  return tom_compute_dist_impl(dA_rows, d_operand, op_rows, d_scale, d_k, n, world, rank, per, tom_type,
+                               tom_denom, out_mode, peer_out, nullptr, 0u, device, stream);
+}
+
+extern "C" int b200w_dev_tom_compute_dist_gated(const double* dA_rows, const void* d_operand,
+                                                int64_t op_rows, const double* d_scale, const double* d_k,
+                                                int64_t n, int world, int rank, int64_t per, int tom_type,
+                                                int tom_denom, int out_mode, void* const* peer_out,
+                                                const uint32_t* d_plane_flags, uint32_t plane_epoch,
+                                                int device, void* stream) {
+  if (!d_plane_flags) return fail(B200W_E_INVALID, "tom_compute_dist_gated: bad args");
+  return tom_compute_dist_impl(dA_rows, d_operand, op_rows, d_scale, d_k, n, world, rank, per, tom_type,
+                               tom_denom, out_mode, peer_out, d_plane_flags, plane_epoch, device, stream);
+}
+
+// Pull the other ranks' operand rows (digit planes, heaviest first, then nothing else: scale and k go first)
+// out of their HBM with the copy engines, and publish each plane's arrival to the contraction kernel.
+typedef CUresult (*StreamWriteValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+
+extern "C" int b200w_dev_tom_pull_planes(void* d_local, void* const* peer_base, int world, int rank, int64_t per,
+                                         int64_t op_rows, int64_t n, uint32_t* d_plane_flags, uint32_t epoch,
+                                         int device, void* copy_stream) {
+  if (!d_local || !peer_base || !d_plane_flags || world < 2 || world > 8 || rank < 0 || rank >= world ||
+      per < 128 || per * world != op_rows)
+    return fail(B200W_E_INVALID, "tom_pull_planes: bad args");
+  if (int e = ensure_device(device)) return e;
+  static StreamWriteValue32Fn write32 = [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &sym, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      sym = nullptr;
+    return (StreamWriteValue32Fn)sym;
+  }();
+  if (!write32) return fail(B200W_E_UNSUPPORTED, "tom_pull_planes: cuStreamWriteValue32 not available");
+  cudaStream_t cs = (cudaStream_t)copy_stream;
+  const int64_t ldn = b200w_padded_n(n);
+  const int64_t plane = op_rows * ldn;
+  const int64_t scale_off = b200w_tom_shared_scale_offset(op_rows, n), k_off = scale_off + op_rows * 8;
+  auto pull = [&](int64_t off, int64_t bytes) -> cudaError_t {
+    for (int q = 1; q < world; ++q) {  // start with the neighbour: the ranks do not all hit one peer first
+      const int src = (rank + q) % world;
+      if ((int64_t)src * per >= n) continue;  // a trailing rank without rows has nothing to give
+      if (!peer_base[src]) return cudaErrorInvalidValue;
+      cudaError_t e = cudaMemcpyAsync((char*)d_local + off + (int64_t)src * per * (bytes / per),
+                                      (const char*)peer_base[src] + off + (int64_t)src * per * (bytes / per), bytes,
+                                      cudaMemcpyDeviceToDevice, cs);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  };
+  B200W_CUDA(pull(scale_off, per * 8));
+  B200W_CUDA(pull(k_off, per * 8));
+  for (int s = B200W_I8_SLICES - 1; s >= 0; --s) {
+    B200W_CUDA(pull((int64_t)s * plane, per * ldn));
+    const CUresult r = write32((CUstream)cs, (CUdeviceptr)(d_plane_flags + s), epoch, 0);
+    if (r != CUDA_SUCCESS) return fail(B200W_E_CUDA, "tom_pull_planes: cuStreamWriteValue32 failed (%d)", (int)r);
+  }
+  return 0;
+}
+
+extern "C" int64_t b200w_tom_shared_scale_offset(int64_t op_rows, int64_t n) {
+  return round_up((int64_t)B200W_I8_SLICES * op_rows * b200w_padded_n(n), 256);
+}
+extern "C" int64_t b200w_tom_shared_bytes(int64_t op_rows, int64_t n) {
+  return b200w_tom_shared_scale_offset(op_rows, n) + 2 * op_rows * 8;
 }
 
 int b200w_dev_intramodular(const double* dA, int64_t n, const int32_t* d_labels,

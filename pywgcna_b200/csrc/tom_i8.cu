@@ -65,6 +65,10 @@ struct I8Params {
   const double* scale_col;  // scale / k of the column operand (= scale / k unless A is asymmetric,
   const double* k_col;      //  TomColumnOperand)
   int32_t nan_mode;         // NaN rows / columns propagate (k = NaN marks them)
+  // sharded run with the exchange overlapped: plane s of the peers' operand rows is in place once
+  // plane_flags[s] has reached plane_epoch (written on the copy stream after the copies of that plane)
+  const unsigned int* plane_flags;
+  unsigned int plane_epoch;
   double* out;           // nrows x n
   double* scratch;       // gridDim.x * 128 * 256
   int64_t n, row0, nrows;
@@ -420,6 +424,24 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
             if (split) atomicAdd(p.sync_ctr, 1u);  // arrival for the next segment
             continue;
           }
+          if (p.plane_flags != nullptr) {
+            // the digit planes of the other ranks arrive heaviest first while this kernel runs (copy engines,
+            // b200w_dev_tom_pull_planes); segments are ordered heaviest weight first, so only the first use
+            // of a plane can actually wait
+            const int need = sgm.s < sgm.t ? sgm.s : sgm.t;  // planes arrive in descending order
+            unsigned int v, spins = 0;
+            uint64_t t0 = 0;
+            while (true) {
+              asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.plane_flags + need) : "memory");
+              if ((int)(v - p.plane_epoch) >= 0) break;
+              if ((++spins & 1023u) == 0) {
+                const uint64_t now = global_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > kWaitLimitNs) __trap();
+              }
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");  // the TMA reads below must see the copied data
+          }
           const int arrive_kb = (sgm.kb1 - p.sync_lead > sgm.kb0) ? sgm.kb1 - p.sync_lead : sgm.kb0;
           for (int kb = sgm.kb0; kb < sgm.kb1; ++kb) {
             if (split && kb == arrive_kb) atomicAdd(p.sync_ctr, 1u);  // arrival for the next segment
@@ -750,7 +772,8 @@ int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t o
                          const double* d_k, int64_t n, int64_t row0, int64_t nrows, int tom_type, int tom_denom,
                          int out_mode, double* d_out, cudaStream_t st, int world, int rank, int64_t per,
                          double* const* peer_out, b200w::TomProgress* progress, int w_min_arg,
-                         const b200w::TomColumnOperand* col) {
+                         const b200w::TomColumnOperand* col, const unsigned int* d_plane_flags,
+                         unsigned int plane_epoch) {
   const int64_t ldn = b200w_padded_n(n);
   if (op_rows > 0x7fffffff || ldn > 0x7fffffff) return fail(B200W_E_UNSUPPORTED, "tom_i8: n too large");
   EncodeTiledFn encode = get_encode_tiled();
@@ -781,6 +804,8 @@ int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t o
   prm.scale_col = (col && col->scale) ? col->scale : d_scale;
   prm.k_col = (col && col->k) ? col->k : d_k;
   prm.nan_mode = col ? col->nan_mode : 0;
+  prm.plane_flags = d_plane_flags;
+  prm.plane_epoch = plane_epoch;
   prm.out = d_out;
   prm.n = n;
   prm.row0 = row0;

@@ -37,6 +37,49 @@ class _DevView:
                                          "version": 3, "strides": None}
 
 
+class SftTable:
+    """The six statistic columns of the reference's soft-threshold table (wgcna.py:924-932), evaluated on
+    first access from the per-power statistics the device computed (``wgcna.fit_table_from_stats``).  Also
+    carries what the device decided: ``device_fit`` ([P, 2]: R^2, exact mean) and ``device_power``; and
+    ``host_power`` = the selection of wgcna.py:945-953 redone on the host table (the tests compare them)."""
+
+    COLUMNS = ("SFT.R.sq", "slope", "truncated R.sq", "mean(k)", "median(k)", "max(k)")
+
+    def __init__(self, event, host_bufs, powers, n, nBreaks, RsquaredCut, MeanCut):
+        self._event, self._bufs = event, host_bufs
+        self.powers, self.n, self.nBreaks = powers, n, nBreaks
+        self.RsquaredCut, self.MeanCut = RsquaredCut, MeanCut
+        self._cols = None
+
+    def _evaluate(self):
+        if self._cols is None:
+            from . import wgcna as W
+
+            self._event.synchronize()
+            h_stats, h_buck, h_fit, h_power, _ = self._bufs
+            self.device_fit = h_fit.numpy().copy()
+            self.device_power = float(h_power[0])
+            vals = W.fit_table_from_stats(h_stats.numpy(), h_buck.numpy(), self.n, self.nBreaks)
+            self._cols = dict(zip(self.COLUMNS, vals))
+            r2, mean = self._cols["SFT.R.sq"], self._cols["mean(k)"]
+            with np.errstate(invalid="ignore"):
+                ind = (r2 > self.RsquaredCut) & (mean <= self.MeanCut)  # wgcna.py:945
+            self.host_power = self.powers[ind].min() if ind.any() else self.powers[np.argsort(r2)[-1]]
+        return self._cols
+
+    def __getitem__(self, name):
+        return self._evaluate()[name]
+
+    def keys(self):
+        return self.COLUMNS
+
+    def __iter__(self):
+        return iter(self.COLUMNS)
+
+    def __len__(self):
+        return len(self.COLUMNS)
+
+
 class DeviceNetwork:
     """Expression matrix resident in HBM; sweep / adjacency / TOM without leaving the device."""
 
@@ -79,6 +122,15 @@ class DeviceNetwork:
         self.planes, self.elt = (1, 8) if elt == 8 else (elt, 1)
         self.fused = (self.world > 1 and self.elt == 1
                       and os.environ.get("B200WGCNA_DIST", "fused") != "rowblock")
+        # operand exchange of the fused mode: "pull" = copy engines fetch the peers' digit planes out of their
+        # HBM (heaviest plane first) while the contraction already runs, gated per plane; "gather" = NCCL
+        # all-gathers before the kernel starts
+        self.pull = (self.fused and bool(self.use_dist)
+                     and os.environ.get("B200WGCNA_EXCHANGE", "pull") == "pull")
+        self._op_raw = None
+        self._peer_op_ptrs = None
+        self._epoch = 0
+        self._gate = None
         self.A = None
         self._sim_in_A = False  # self.A holds the similarity the last sweep left (see sweep / adjacency)
         # sweep() leaves this rank's rows of the similarity in the adjacency buffer (overwriting a block an
@@ -99,6 +151,8 @@ class DeviceNetwork:
                 self.lib.b200w_ipc_close(p, self.device)
             if self._T_raw:
                 self.lib.b200w_dev_free(self._T_raw, self.device)
+            if self._op_raw:
+                self.lib.b200w_dev_free(self._op_raw, self.device)
         except Exception:
             pass
 
@@ -151,52 +205,98 @@ class DeviceNetwork:
         return kT[:self.n].T.contiguous()
 
     def sft(self, powers, nBreaks: int = 10, RsquaredCut: float = 0.9, MeanCut: float = 100):
-        """Device-resident ``pickSoftThreshold`` (wgcna.py:873-953): sweep, then histograms, medians and
-        exact mantissa sums on the device; 2 x P ten-point regressions on the host.  Returns
-        (selected power, dict of the six table columns)."""
-        from . import wgcna as W
-
+        """Device-resident ``pickSoftThreshold`` (wgcna.py:873-953): sweep, then histograms, medians, exact
+        mantissa sums, the regression R^2 and the power selection (:945-953) on the device
+        (``b200w_dev_sft_select``).  Nothing here waits for the GPU: returns ``(power, table)`` where ``power``
+        is a 0-dim float64 DEVICE tensor that ``adjacency()`` reads in place, and ``table`` is a lazy mapping
+        of the six columns of the reference's table -- its first access waits for the asynchronous copy of the
+        per-power statistics and runs the 2 x P ten-point regressions on the host (float64, the reference's
+        arithmetic), typically while the GPU is busy with the adjacency and the TOM."""
         pv = np.sort(np.asarray(powers))
         k = self.sweep(pv)  # [P, n]
         P = len(pv)
-        if not hasattr(self, "_sft_bufs") or self._sft_bufs[0].shape[0] != P or self._sft_bufs[3] != nBreaks:
+        key = (P, nBreaks)
+        if getattr(self, "_sft_key", None) != key:
             E = self.lib.b200w_sft_exp_buckets()
-            self._sft_bufs = (torch.empty((P, 4 + 2 * nBreaks), dtype=torch.float64, device=self.dev),
-                              torch.empty((P, E, 2), dtype=torch.int64, device=self.dev),
-                              (torch.empty((P, 4 + 2 * nBreaks), dtype=torch.float64).pin_memory(),
-                               torch.empty((P, E, 2), dtype=torch.int64).pin_memory()), nBreaks)
-        d_stats, d_buck, (h_stats, h_buck), _ = self._sft_bufs
-        L.check(self.lib.b200w_dev_sft_stats(k.data_ptr(), P, self.n, k.stride(0), nBreaks, d_stats.data_ptr(),
-                                             d_buck.data_ptr(), self.device, self._stream()))
+            f64, i64 = torch.float64, torch.int64
+            self._sft_dev = (torch.empty((P, 4 + 2 * nBreaks), dtype=f64, device=self.dev),
+                             torch.empty((P, E, 2), dtype=i64, device=self.dev),
+                             torch.empty((P, 2), dtype=f64, device=self.dev),
+                             torch.empty(2, dtype=f64, device=self.dev),
+                             torch.empty(P, dtype=f64, device=self.dev))
+            self._sft_host = (torch.empty((P, 4 + 2 * nBreaks), dtype=f64).pin_memory(),
+                              torch.empty((P, E, 2), dtype=i64).pin_memory(),
+                              torch.empty((P, 2), dtype=f64).pin_memory(), torch.empty(2, dtype=f64).pin_memory(),
+                              torch.empty(P, dtype=f64).pin_memory())
+            self._sft_key = key
+            self._sft_powers = None
+        d_stats, d_buck, d_fit, d_power, d_powers = self._sft_dev
+        h_stats, h_buck, h_fit, h_power, h_powers = self._sft_host
+        if self._sft_powers is None or not np.array_equal(self._sft_powers, pv):
+            h_powers.copy_(torch.from_numpy(pv.astype(np.float64)))
+            d_powers.copy_(h_powers, non_blocking=True)
+            self._sft_powers = pv.copy()
+        L.check(self.lib.b200w_dev_sft_select(k.data_ptr(), P, self.n, k.stride(0), nBreaks, d_powers.data_ptr(),
+                                              float(RsquaredCut), float(MeanCut), d_stats.data_ptr(),
+                                              d_buck.data_ptr(), d_fit.data_ptr(), d_power.data_ptr(),
+                                              self.device, self._stream()))
         h_stats.copy_(d_stats, non_blocking=True)
         h_buck.copy_(d_buck, non_blocking=True)
-        torch.cuda.current_stream(self.dev).synchronize()
-        r2, slope, r2adj, mean, med, mx = W.fit_table_from_stats(h_stats.numpy(), h_buck.numpy(), self.n, nBreaks)
-        with np.errstate(invalid="ignore"):
-            ind = (r2 > RsquaredCut) & (mean <= MeanCut)  # wgcna.py:945
-        power = pv[ind].min() if ind.any() else pv[np.argsort(r2)[-1]]
-        return power, {"SFT.R.sq": r2, "slope": slope, "truncated R.sq": r2adj, "mean(k)": mean,
-                       "median(k)": med, "max(k)": mx}
+        h_fit.copy_(d_fit, non_blocking=True)
+        h_power.copy_(d_power, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        return d_power[0], SftTable(ev, self._sft_host, pv, self.n, nBreaks, RsquaredCut, MeanCut)
 
-    def adjacency(self, power: float) -> torch.Tensor:
-        """This rank's row block of the adjacency (wgcna.py:1097-1111), kept in HBM."""
+    def adjacency(self, power) -> torch.Tensor:
+        """This rank's row block of the adjacency (wgcna.py:1097-1111), kept in HBM.  ``power`` is a number
+        or the device scalar ``sft()`` returned (then the kernels read it from HBM: no host round trip)."""
         if not self._standardized:
             self.standardize()
         if self.A is None:
             self.A = torch.empty((max(self.nrows, 1), self.n), dtype=torch.float64, device=self.dev)
+        on_dev = isinstance(power, torch.Tensor) and power.is_cuda
+        if on_dev:
+            assert power.dtype == torch.float64 and power.device == self.dev
         if self._sim_in_A:
             self._sim_in_A = False  # consumed: the buffer turns into the adjacency
-            L.check(self.lib.b200w_dev_adjacency_from_similarity(self.A.data_ptr(), self.nrows, self.n,
-                                                                 float(power), self.device, self._stream()))
+            if self.nrows == 0:
+                return self.A[:0]
+            if on_dev:
+                L.check(self.lib.b200w_dev_adjacency_from_similarity_dp(self.A.data_ptr(), self.nrows, self.n,
+                                                                        power.data_ptr(), self.device,
+                                                                        self._stream()))
+            else:
+                L.check(self.lib.b200w_dev_adjacency_from_similarity(self.A.data_ptr(), self.nrows, self.n,
+                                                                     float(power), self.device, self._stream()))
             return self.A[:self.nrows]
         if self.nrows > 0:
-            L.check(self.lib.b200w_dev_adjacency(self.Z.data_ptr(), self.bad.data_ptr(), self.m, self.n, self.net,
-                                                 float(power), self.row0, self.nrows, self.A.data_ptr(),
-                                                 self.device, self._stream()))
+            if on_dev:
+                L.check(self.lib.b200w_dev_adjacency_dp(self.Z.data_ptr(), self.bad.data_ptr(), self.m, self.n,
+                                                        self.net, power.data_ptr(), self.row0, self.nrows,
+                                                        self.A.data_ptr(), self.device, self._stream()))
+            else:
+                L.check(self.lib.b200w_dev_adjacency(self.Z.data_ptr(), self.bad.data_ptr(), self.m, self.n,
+                                                     self.net, float(power), self.row0, self.nrows,
+                                                     self.A.data_ptr(), self.device, self._stream()))
         return self.A[:self.nrows]
 
     # -- TOM -----------------------------------------------------------------------------------
     def _operand(self):
+        if self._op is None and self.pull:
+            # planes, scale and k in one cudaMalloc allocation that the peers map through CUDA IPC
+            nbytes = self.lib.b200w_tom_shared_bytes(self.op_rows, self.n)
+            off = self.lib.b200w_tom_shared_scale_offset(self.op_rows, self.n)
+            p = C.c_void_p()
+            L.check(self.lib.b200w_dev_malloc(nbytes, self.device, C.byref(p)))
+            self._op_raw = p.value
+            whole = torch.as_tensor(_DevView(p.value, (nbytes,), "|u1"), device=self.dev)
+            whole.zero_()
+            self._op = whole[:self.planes * self.op_rows * self.ldn].view(self.planes, self.op_rows, self.ldn)
+            self._scale = whole[off:off + self.op_rows * 8].view(torch.float64)
+            self._k = whole[off + self.op_rows * 8:off + self.op_rows * 16].view(torch.float64)
+            self._plane_flags = torch.zeros(8, dtype=torch.int32, device=self.dev)
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
         if self._op is None:
             self._op = torch.zeros((self.planes, self.op_rows, self.ldn * self.elt), dtype=torch.uint8, device=self.dev)
             self._scale = torch.zeros(self.op_rows, dtype=torch.float64, device=self.dev)
@@ -217,32 +317,43 @@ class DeviceNetwork:
                 self.T = torch.empty((rows, self.n), dtype=torch.float64, device=self.dev)
         return self.T
 
-    def ipc_handle(self) -> bytes:
+    def ipc_handle(self, raw=None) -> bytes:
         self._out()
         h = C.create_string_buffer(64)
-        L.check(self.lib.b200w_ipc_export(self._T_raw, h))
+        L.check(self.lib.b200w_ipc_export(self._T_raw if raw is None else raw, h))
         return h.raw
 
     def connect_peers(self, ptrs=None):
-        """Table of every rank's TOM block as seen from this GPU.  ``ptrs`` (tests: ranks emulated in one
-        process) are used as they are; otherwise CUDA IPC handles are exchanged over the process group."""
+        """Table of every rank's TOM block (and, in pull mode, operand allocation) as seen from this GPU.
+        ``ptrs`` (tests: ranks emulated in one process) are used as they are; otherwise CUDA IPC handles are
+        exchanged over the process group -- a collective: every rank calls it, also one without rows."""
         self._out()
         if ptrs is None:
             import torch.distributed as dist
 
-            mine = torch.frombuffer(bytearray(self.ipc_handle()), dtype=torch.uint8).to(self.dev)
-            allh = torch.zeros((self.world, 64), dtype=torch.uint8, device=self.dev)
+            self._operand()
+            handles = self.ipc_handle() + (self.ipc_handle(self._op_raw) if self.pull else bytes(64))
+            mine = torch.frombuffer(bytearray(handles), dtype=torch.uint8).to(self.dev)
+            allh = torch.zeros((self.world, 128), dtype=torch.uint8, device=self.dev)
             dist.all_gather_into_tensor(allh, mine, group=self.group)
             allh = allh.cpu().numpy()
-            ptrs = []
+            ptrs, op_ptrs = [], []
             for r in range(self.world):
                 if r == self.rank:
                     ptrs.append(self._T_raw)
-                else:
-                    p = C.c_void_p()
-                    L.check(self.lib.b200w_ipc_open(allh[r].tobytes(), self.device, C.byref(p)))
-                    self._peer_open.append(p.value)
-                    ptrs.append(p.value)
+                    op_ptrs.append(self._op_raw or 0)
+                    continue
+                p = C.c_void_p()
+                L.check(self.lib.b200w_ipc_open(allh[r, :64].tobytes(), self.device, C.byref(p)))
+                self._peer_open.append(p.value)
+                ptrs.append(p.value)
+                if self.pull:
+                    q = C.c_void_p()
+                    L.check(self.lib.b200w_ipc_open(allh[r, 64:].tobytes(), self.device, C.byref(q)))
+                    self._peer_open.append(q.value)
+                    op_ptrs.append(q.value)
+            if self.pull:
+                self._peer_op_ptrs = (C.c_void_p * self.world)(*[int(p) for p in op_ptrs])
         self._peer_ptrs = (C.c_void_p * self.world)(*[int(p) for p in ptrs])
 
     def tom_prepare(self, A_rows: torch.Tensor | None = None):
@@ -257,21 +368,54 @@ class DeviceNetwork:
                                                    op.data_ptr(), self.op_rows, self._scale.data_ptr(),
                                                    self._k.data_ptr(), self.device, self._stream()))
 
+    def _sync_flag(self):
+        if not hasattr(self, "_flag"):
+            self._flag = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        return self._flag
+
     def tom_exchange(self):
-        if self.world > 1:
-            for p in range(self.planes):
-                self._all_gather_rows(self._op[p])
-            self._all_gather_rows(self._k)
-            self._all_gather_rows(self._scale)
+        if self.world == 1:
+            return
+        if self.pull:
+            import torch.distributed as dist
+
+            if self._peer_ptrs is None:
+                self.connect_peers()
+            # every rank's rows of the operand are final once this tiny all-reduce has passed (stream order);
+            # from then on the copy engines pull the peers' rows while the contraction below already runs
+            dist.all_reduce(self._sync_flag(), group=self.group)
+            main = torch.cuda.current_stream(self.dev)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self._copy_stream.wait_event(ev)
+            self._epoch = (self._epoch + 1) & 0x7fffffff
+            L.check(self.lib.b200w_dev_tom_pull_planes(self._op_raw, self._peer_op_ptrs, self.world, self.rank,
+                                                       self.per, self.op_rows, self.n,
+                                                       self._plane_flags.data_ptr(), self._epoch, self.device,
+                                                       self._copy_stream.cuda_stream))
+            self._gate = self._epoch
+            return
+        for p in range(self.planes):
+            self._all_gather_rows(self._op[p])
+        self._all_gather_rows(self._k)
+        self._all_gather_rows(self._scale)
 
     def tom_compute(self, TOMType: str = "signed", TOMDenom: str = "min", out_mode: int = L.OUT_TOM):
         tt, td = L.TOM_TYPES.index(TOMType), L.TOM_DENOMS.index(TOMDenom)
         T = self._out()
         if self.fused and self._peer_ptrs is None:
             self.connect_peers()  # a collective: every rank takes part, also one without rows
+        gate, self._gate = self._gate, None
         if self.nrows == 0:
+            if gate is not None:  # nothing to compute, but the pulls must not outlive this step
+                torch.cuda.current_stream(self.dev).wait_stream(self._copy_stream)
             return T[:0]
-        if self.fused:
+        if self.fused and gate is not None:
+            L.check(self.lib.b200w_dev_tom_compute_dist_gated(
+                self._A_rows.data_ptr(), self._op.data_ptr(), self.op_rows, self._scale.data_ptr(),
+                self._k.data_ptr(), self.n, self.world, self.rank, self.per, tt, td, out_mode, self._peer_ptrs,
+                self._plane_flags.data_ptr(), gate, self.device, self._stream()))
+        elif self.fused:
             L.check(self.lib.b200w_dev_tom_compute_dist(self._A_rows.data_ptr(), self._op.data_ptr(), self.op_rows,
                                                         self._scale.data_ptr(), self._k.data_ptr(), self.n,
                                                         self.world, self.rank, self.per, tt, td, out_mode,
@@ -289,9 +433,7 @@ class DeviceNetwork:
         if self.fused and self.use_dist:
             import torch.distributed as dist
 
-            if not hasattr(self, "_flag"):
-                self._flag = torch.zeros(1, dtype=torch.float32, device=self.dev)
-            dist.all_reduce(self._flag, group=self.group)
+            dist.all_reduce(self._sync_flag(), group=self.group)
 
     def tom(self, TOMType: str = "signed", TOMDenom: str = "min", out_mode: int = L.OUT_TOM,
             A_rows: torch.Tensor | None = None) -> torch.Tensor:
@@ -330,19 +472,24 @@ def network_blocks(datExpr, powerVector=None, networkType="unsigned", TOMType="s
     L.check(lib.b200w_dev_upload(Xd.data_ptr(), L.hptr(X), X.nbytes, dev, st))
     net = DeviceNetwork(Xd, device=dev, networkType=networkType, precision=precision)
     sft = None
-    if power is None:
+    picked = power is None
+    if picked:
         pv = np.sort(np.asarray(list(range(1, 11)) + list(range(1, 21, 2)) if powerVector is None else powerVector))
         power, cols = net.sft(pv, nBreaks=nBreaks, RsquaredCut=RsquaredCut, MeanCut=MeanCut)
-        names = ["Power", "SFT.R.sq", "slope", "truncated R.sq", "mean(k)", "median(k)", "max(k)"]
-        sft = pd.DataFrame({"Power": pv, **{c: cols[c] for c in names[1:]}}, columns=names).astype(object)
-    A = net.adjacency(float(power))
-    res = {"power": power, "sft": sft, "rows": (net.row0, net.nrows)}
+    A = net.adjacency(power)  # a device scalar after sft(): the chain below is enqueued without waiting
+    res = {"rows": (net.row0, net.nrows)}
     if return_adjacency:
         a_host = L.result_empty((net.nrows, n))
         if net.nrows:
             L.check(lib.b200w_dev_download(L.hptr(a_host), A.data_ptr(), a_host.nbytes, dev, st))
         res["adjacency"] = a_host
     T = net.tom(TOMType=TOMType, TOMDenom=TOMDenom, out_mode=out_mode)
+    if picked:
+        # the host half of the soft-threshold table (2 x P ten-point regressions) runs while the GPU works
+        names = ["Power", "SFT.R.sq", "slope", "truncated R.sq", "mean(k)", "median(k)", "max(k)"]
+        sft = pd.DataFrame({"Power": pv, **{c: cols[c] for c in names[1:]}}, columns=names).astype(object)
+        power = type(pv[0])(cols.device_power)
+    res["power"], res["sft"] = power, sft
     t_host = L.result_empty((net.nrows, n))
     if net.nrows:
         L.check(lib.b200w_dev_download(L.hptr(t_host), T.data_ptr(), t_host.nbytes, dev, st))

@@ -341,6 +341,14 @@ def test_device_sft_statistics(gpu, n):
     np.testing.assert_allclose(tab["truncated R.sq"], r2adj, rtol=1e-9, atol=1e-11)
     p_ref, _ = O.pickSoftThreshold(pd.DataFrame(X), networkType="signed hybrid", powerVector=powers, faithful=False)
     assert int(power) == int(p_ref)
+    # what the device decided without the host (b200w_dev_sft_select): the exactly rounded mean bit for bit, the
+    # regression R^2 to rounding, and the same selection as wgcna.py:945-953 on the host table
+    assert np.array_equal(tab.device_fit[:, 1], mean)
+    np.testing.assert_allclose(tab.device_fit[:, 0], r2, rtol=1e-11, atol=1e-13)
+    assert tab.device_power == float(tab.host_power) == float(p_ref)
+    for cut, mcut in ((0.0, 1e9), (2.0, 100.0), (0.5, 30.0)):  # first branch / argmax branch / both limits active
+        pw, tb = net.sft(powers, RsquaredCut=cut, MeanCut=mcut)
+        assert float(pw) == float(tb.host_power), (cut, mcut)
 
 
 @pytest.mark.parametrize("net", ["unsigned", "signed", "signed hybrid"])
