@@ -442,7 +442,7 @@ static int sft_stats_impl(const double* d_k, int P, int64_t n, int64_t ldk, int 
   if (int e = ensure_device(device)) return e;
   if (n >= (1LL << 20)) return fail(B200W_E_UNSUPPORTED, "sft_stats: more than 2^20 - 1 genes");
   // rows up to ~21k connectivities are staged in shared memory (one global read instead of ten)
-  static const size_t kCacheMax = 170 * 1024, kBucketBytes = (size_t)kExpBuckets * kPieces * sizeof(int);
+  static const size_t kCacheMax = 164 * 1024, kBucketBytes = (size_t)kExpBuckets * kPieces * sizeof(int);
   static_assert(kBucketBytes % sizeof(double) == 0, "row cache alignment");
   const size_t row_bytes = (size_t)n * sizeof(double);
   const int cached = row_bytes <= kCacheMax ? 1 : 0;
