@@ -562,6 +562,9 @@ def measure_ours(args, wl, steps, warmup, world, rank, local, with_e2e, with_fas
                           "reference's three calls"}
         else:
             e2e = e2e_fused
+        from pywgcna_b200.device import release_workspace
+
+        release_workspace()
         lib.b200w_dev_trim()
         lib.b200w_host_trim()
     else:

@@ -160,6 +160,15 @@ void b200w_host_trim(void);
  * between calls instead of cudaMalloc / cudaFree each time; this releases the cached ones. */
 void b200w_dev_trim(void);
 
+/* Arithmetic of the correlation product Z Z^T behind the sweep and the adjacency (np.corrcoef at wgcna.py:882,
+ * :1097), process wide:
+ *   B200W_PREC_I8  (default, = B200W_PREC_AUTO; env B200WGCNA_CORR_PRECISION=i8): tcgen05 kind::i8 MMAs on six
+ *                  int8 digit planes of the standardised genes (46-bit fixed point per gene, exact int32
+ *                  accumulation, TMA fed; corr_i8.cu) -- max-abs error against np.corrcoef ~2e-13;
+ *   B200W_PREC_F64 (env ...=f64): FP64 DMMA (mma.sync), ~1e-15.
+ * Step lists other than 1 / 2 between consecutive powers always use the FP64 engine. */
+int b200w_set_correlation_precision(int precision);
+
 /* ---------------------------------------------------------------- device entry points */
 
 /* bytes of scratch the dev_* calls need are allocated stream-ordered internally. */

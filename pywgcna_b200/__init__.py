@@ -6,9 +6,9 @@ signatures.  ``install()`` rebinds them on ``PyWGCNA.wgcna.WGCNA``.
 """
 from .wgcna import (TOMDenoms, TOMTypes, TOMsimilarity, TomSimilarityFromAdj, adjacency, adjacencyTypes,
                     calBlockSize, checkAdjMat, checkSimilarity, connectivity, dissTOM, install, intramodularConnectivity, network,
-                    network_blocks, networkTypes, pickSoftThreshold, scaleFreeFitIndex, signedKME, softConnectivity, uninstall)
+                    network_blocks, networkTypes, pickSoftThreshold, scaleFreeFitIndex, set_correlation_precision, signedKME, softConnectivity, uninstall)
 
 __version__ = "0.1.0"
 __all__ = ["TOMDenoms", "TOMTypes", "TOMsimilarity", "TomSimilarityFromAdj", "adjacency", "adjacencyTypes",
            "calBlockSize", "checkAdjMat", "checkSimilarity", "connectivity", "dissTOM", "install", "intramodularConnectivity",
-           "network", "network_blocks", "networkTypes", "pickSoftThreshold", "scaleFreeFitIndex", "signedKME", "softConnectivity", "uninstall"]
+           "network", "network_blocks", "networkTypes", "pickSoftThreshold", "scaleFreeFitIndex", "set_correlation_precision", "signedKME", "softConnectivity", "uninstall"]

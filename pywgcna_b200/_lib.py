@@ -56,6 +56,7 @@ SIGNATURES = {
     "b200w_host_free": (None, [C.c_void_p]),
     "b200w_host_trim": (None, []),
     "b200w_dev_trim": (None, []),
+    "b200w_set_correlation_precision": (_int, [_int]),
     "b200w_padded_k": (_i64, [_i64]),
     "b200w_dev_standardize": (_int, [_dp, _i64, _i64, _dp, _dp, _int, _dp]),
     "b200w_dev_sweep": (_int, [_dp, _dp, _i64, _i64, _dp, _int, _int, _i64, _i64, _dp, _int, _dp]),

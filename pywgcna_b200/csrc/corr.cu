@@ -2,6 +2,7 @@
 // Reference arithmetic: np.corrcoef (numpy lib/_function_base_impl.py cov/corrcoef) as called at
 // PyWGCNA/wgcna.py:882 and :1097; sweep wgcna.py:884-916; adjacency wgcna.py:1102-1111.
 #include "gemm_f64.cuh"
+#include "sweep_common.cuh"
 
 namespace b200w {
 
@@ -114,50 +115,12 @@ __device__ __forceinline__ void park_acc(const AccF64& acc, double* wt, int lane
 // matrix element stays what it was; the saving is the MMA half of the shared pipe.
 // -------------------------------------------------------------------------------------------
 constexpr int kSweepStages = 3;
-constexpr int kSweepMaxP = 20;   // 3 ring slots + 2 x 20 x 64 sums: two CTAs fit one SM
+// (kSweepMaxP = 20: 3 ring slots + 2 x 20 x 64 sums let two CTAs fit one SM)
 constexpr int kSweepPitch = 41;  // doubles; odd, so the transposed re-read of the parked tile is 2-way at worst
 #ifndef B200W_SWEEP_ROWS
 #define B200W_SWEEP_ROWS 8
 #endif
 constexpr int kSweepRows = B200W_SWEEP_ROWS;  // rows of a column in flight per lane: independent chains
-
-struct SweepParams {
-  const double* Z;
-  const uint8_t* bad;
-  int64_t n, ldk;
-  int64_t col0, ncols;  // genes whose connectivity this launch produces
-  int64_t RT, T;        // row tiles, total tiles (CT * RT)
-  int P;
-  int net_type;
-  int max_seg;          // partial slots per CTA
-  int simple_steps;     // every istep is 1 or 2
-  double* partial;      // [gridDim.x][max_seg][P][64]
-  double* sim;          // optional output: the transformed similarity as adjacency() sees it (below) ...
-  int sim_transposed;   // ... 0: sim[i * n + j] (whole matrix), 1: sim[(j - col0) * n + i] (this column block
-                        //     as the row block of the symmetric matrix: what a rank of the sharded path keeps)
-  int symmetric;        // whole matrix, only tiles on and above the diagonal (see sweep_kernel)
-  double* rowpart;      // symmetric: [tile][P][128] row sums of the tiles above the diagonal
-  double step[kSweepMaxP];
-  int istep[kSweepMaxP];
-};
-
-__host__ __device__ __forceinline__ void sweep_range(int64_t T, int64_t G, int64_t b, int64_t& t0, int64_t& t1) {
-  t0 = T * b / G;
-  t1 = T * (b + 1) / G;
-}
-
-// Symmetric sweep: column tile jt (64 wide, inside the 128-block jt / 2) only takes the row tiles 0 .. jt / 2,
-// enumerated column-major like the full grid.  sym_offset(jt) = number of tiles before column tile jt.
-__host__ __device__ __forceinline__ int64_t sym_offset(int64_t jt) {
-  const int64_t q = jt >> 1, r = jt & 1;
-  return (q + 1) * (q + r);
-}
-__host__ __device__ __forceinline__ int64_t sym_col_of(int64_t t) {  // largest jt with sym_offset(jt) <= t
-  int64_t jt = 2 * (int64_t)sqrt((double)t);
-  while (jt > 0 && sym_offset(jt) > t) --jt;
-  while (sym_offset(jt + 1) <= t) ++jt;
-  return jt;
-}
 
 __global__ void __launch_bounds__(kNarrowThreads, 2) sweep_kernel(const SweepParams prm) {
   constexpr int kBN = kNarrowBN;
@@ -430,30 +393,6 @@ constexpr int kAdjStages = 3;   // narrow-engine ring slots of the adjacency (tw
 constexpr int kCrossStages = 4;  // wide-engine ring slots of the cross-correlation
 constexpr int kAdjPitch = 33;    // odd: the transposed (mirror) reads of the parked tile stay 2-way at worst
 
-// integer powers up to 64 are evaluated by repeated squaring (0: use pow())
-__host__ __device__ __forceinline__ int small_int_power(double power) {
-  return (power == (double)(int)power && power >= 1.0 && power <= 64.0) ? (int)power : 0;
-}
-
-// s ** e by binary exponentiation for four values at once (same multiplication order for every value, so
-// a symmetric pair of correlations gives bitwise equal adjacencies)
-__device__ __forceinline__ void int_pow4(double (&s)[4], int e) {
-  double r[4] = {1.0, 1.0, 1.0, 1.0};
-#pragma unroll 1
-  while (true) {
-    if (e & 1) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) r[u] *= s[u];
-    }
-    e >>= 1;
-    if (!e) break;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) s[u] *= s[u];
-  }
-#pragma unroll
-  for (int u = 0; u < 4; ++u) s[u] = r[u];
-}
-
 // tiles_n counts 128-wide column tiles; a CTA takes the left or right 64 columns of one tile.
 __global__ void __launch_bounds__(kNarrowThreads, 2)
 adjacency_kernel(const double* __restrict__ Z, const uint8_t* __restrict__ bad, int64_t n,
@@ -723,7 +662,6 @@ static int sweep_impl(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t
   const int64_t CT = (ncols + kBN - 1) / kBN, RT = (n + kBM - 1) / kBM;
   int sms = 0;
   B200W_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-  const int64_t resident = 2 * (int64_t)sms;
   static const bool sym_allowed = [] {
     const char* e = getenv("B200W_SWEEP_SYMMETRIC");
     return !(e && e[0] == '0');
@@ -752,6 +690,10 @@ static int sweep_impl(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t
       prm.istep[q] = (s == (double)(int)s && s >= 1.0 && s <= 4.0) ? (int)s : 0;
       if (prm.istep[q] != 1 && prm.istep[q] != 2) prm.simple_steps = 0;
     }
+    // the tcgen05 engine (corr_i8.cu) takes every plain chain; other step lists stay on the DMMA engine
+    const bool use_i8 = prm.simple_steps && corr_i8_enabled(m, n);
+    const int64_t resident = (use_i8 ? 1 : 2) * (int64_t)sms;  // persistent CTAs per launch
+    prm.adj_power = 1.0; prm.adj_ipower = 1; prm.d_adj_power = nullptr; prm.zscale = nullptr;
     // whole matrix and a plain chain: only the tiles on and above the diagonal
     bool symmetric = sym_allowed && col0 == 0 && ncols == n && prm.simple_steps;
     if (symmetric) {  // the per-tile row-sum slots must stay a modest part of the device memory
@@ -778,9 +720,13 @@ static int sweep_impl(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t
       B200W_CUDA(rowpart.alloc((size_t)T * Pc * kBM * sizeof(double), st));
       prm.rowpart = rowpart.as<double>();
     }
-    const size_t smem = Narrow::smem_bytes(kSweepStages) + (size_t)2 * Pc * kBN * 8;
-    sweep_kernel<<<G, kNarrowThreads, smem, st>>>(prm);
-    B200W_LAUNCHED();
+    if (use_i8) {
+      if (int e = sweep_i8_launch(prm, m, CT, Pc, G, device, st)) return e;
+    } else {
+      const size_t smem = Narrow::smem_bytes(kSweepStages) + (size_t)2 * Pc * kBN * 8;
+      sweep_kernel<<<G, kNarrowThreads, smem, st>>>(prm);
+      B200W_LAUNCHED();
+    }
     dim3 rgrid((unsigned)CT, (unsigned)Pc);
     if (symmetric)
       sweep_reduce_sym_kernel<<<rgrid, kBN, 0, st>>>(prm.partial, prm.rowpart, G, max_seg, Pc, CT, T, n,
@@ -816,6 +762,21 @@ static int adjacency_impl(const double* dZ, const uint8_t* d_bad, int64_t m, int
   if (net_type < 0 || net_type > 2) return fail(B200W_E_INVALID, "adjacency: bad network type");
   if (int e = ensure_device(device)) return e;
   cudaStream_t st = (cudaStream_t)stream;
+  if (corr_i8_enabled(m, n) && row0 % kSweepBN == 0) {
+    // tcgen05 engine: the sweep's tile walk without a chain (P = 0), the output written as s ** power
+    int sms = 0;
+    B200W_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    SweepParams prm = {};
+    prm.Z = dZ; prm.bad = d_bad; prm.n = n; prm.ldk = b200w_padded_k(m); prm.col0 = row0; prm.ncols = nrows;
+    prm.RT = (n + kBM - 1) / kBM; prm.P = 0; prm.net_type = net_type; prm.simple_steps = 1;
+    prm.sim = dA; prm.symmetric = (row0 == 0 && nrows == n) ? 1 : 0; prm.sim_transposed = prm.symmetric ? 0 : 1;
+    prm.adj_power = power; prm.adj_ipower = small_int_power(power); prm.d_adj_power = d_power;
+    const int64_t CT = (nrows + kSweepBN - 1) / kSweepBN;
+    prm.T = prm.symmetric ? sym_offset(CT) : CT * prm.RT;
+    prm.max_seg = 1;
+    const int G = (int)(prm.T < sms ? prm.T : sms);
+    return sweep_i8_launch(prm, m, CT, 0, G, device, st);
+  }
   const size_t smem = Narrow::smem_bytes(kAdjStages);
   B200W_CUDA(cudaFuncSetAttribute(adjacency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));

@@ -1,0 +1,614 @@
+// K1 on the 5th-generation tensor cores: the standardise-and-correlate product Z Z^T of the soft-threshold sweep
+// and of the adjacency (np.corrcoef at PyWGCNA/wgcna.py:882 and :1097) as tcgen05 kind::i8 MMAs fed by TMA, with
+// the epilogues of corr.cu (clip -> transform -> power chain / s ** power, wgcna.py:884-916 and :1102-1111) fused.
+//
+// Arithmetic.  tcgen05 has no f64 kind, so -- as for the TOM contraction (tom_i8.cu) -- the product is formed
+// exactly in integers: every standardised gene (a unit-norm row of Z, |z| <= 1) is scaled by 2^(46 - e_i), e_i
+// the binary exponent of its largest magnitude, rounded to a 46-bit integer and cut into S = 6 balanced base-256
+// digits (int8 planes).  cor_ij = 2^(e_i + e_j - 92) sum_{s,t} 256^(s+t) sum_k d^s_ik d^t_jk ; each inner sum is an
+// s8 x s8 GEMM accumulated exactly in int32.  The 21 digit pairs of weight w = s + t >= 5 are kept (the dropped
+// ones are below 2^-40 of a unit correlation); the pairs of one weight share one TMEM accumulator, so a tile
+// holds SIX 128 x 64 accumulators (384 TMEM columns) and the epilogue combines them once:
+// ((((a10 * 256 + a9) * 256 + a8) ... ) * 256 + a5) * 2^40 * 2^(e_i + e_j - 92), every factor a power of two, so
+// cor_ij and cor_ji are bitwise equal and do not depend on the tile schedule or on the number of GPUs.
+// Measured against np.corrcoef: <= 2e-13 (tests/test_gpu_round2.py).
+//
+// Kernel (persistent, one CTA per SM, 192 threads):
+//   warp 4     TMA producer: per 64-byte K step ONE box {64 B, 128 rows, 6 planes} of the row genes and one
+//              {64 B, 64 rows, 6 planes} of the column genes (SWIZZLE_64B), 2-stage ring of 72 KB -- all 21
+//              pair products of a K step are issued from the same staged bytes (36 B/clk of L2 traffic per SM
+//              instead of 125 with a stage per pair)
+//   warp 5     TMEM allocation (512 columns) and MMA issue: 21 pairs x 2 tcgen05.mma M128 N64 K32 per stage
+//   warps 0-3  epilogue: drain the six accumulators (tcgen05.ld 32x32b.x16), combine, park the float64 tile in
+//              shared memory, release TMEM (the MMAs of the next tile run under the rest), then the epilogue of
+//              corr.cu's sweep_kernel on the parked tile: lane <-> column, power chain with the P column sums in
+//              registers, second pass with lane <-> row for tiles above the diagonal (symmetric schedule),
+//              optional similarity / adjacency output
+#include <cuda.h>
+
+#include "sweep_common.cuh"
+
+namespace b200w {
+
+constexpr int kZS = 6;                              // digit planes of Z
+constexpr int kZBits = 8 * kZS - 2;                 // 46
+constexpr int kZWmin = 5;                           // lowest digit-pair weight kept
+constexpr int kZAcc = 2 * (kZS - 1) - kZWmin + 1;   // 6 accumulators, weights 5 .. 10
+constexpr int kCKB = 64;                            // K bytes per stage
+constexpr int kCStages = 2;
+constexpr int kCThreads = 192;                      // warps 0-3 epilogue, 4 TMA, 5 MMA
+constexpr int kCAStage = kZS * kSweepBM * kCKB;     // 49152
+constexpr int kCBStage = kZS * kSweepBN * kCKB;     // 24576
+constexpr int kCStageBytes = kCAStage + kCBStage;   // 73728
+constexpr int kParkPitch = 65;                      // doubles; odd: row- and column-wise reads are conflict free
+constexpr int kParkDoubles = kSweepBM * kParkPitch;
+
+struct __align__(8) CorrBars {
+  uint64_t full[kCStages], empty[kCStages], acc_full, acc_empty;
+  uint32_t tmem_base;
+};
+constexpr size_t kCorrSmem = (size_t)kCStages * kCStageBytes + (size_t)kParkDoubles * 8 + sizeof(CorrBars) + 1024;
+
+// ---- PTX wrappers (cta_group::1 only) ---------------------------------------------------------------------
+namespace tc {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ uint64_t global_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// bounded wait (20 s of wall time): a protocol bug ends as a trapped launch, never as a hung GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 4095u) == 0) {
+      const uint64_t now = global_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 20ull * 1000ull * 1000ull * 1000ull) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                       uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void ld_32x32_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// K-major SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address [0,14) >> 4,
+// LBO [16,30) (unused for swizzled K-major, 1), SBO [32,46) = 8 rows * 64 B = 512 B, version [46,48) = 1,
+// layout type [61,64) = 4 (SWIZZLE_64B).  Tiles are 512-byte aligned.
+__device__ __forceinline__ uint64_t make_sw64_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+// instruction descriptor: c_format [4,6) = 2 (S32), a/b format [7,10) / [10,13) = 1 (signed int8), K-major both,
+// n_dim [17,23) = N >> 3, m_dim [24,29) = M >> 4
+__host__ __device__ constexpr uint32_t make_i8_idesc(int M, int N) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+}  // namespace tc
+
+// ---- operand preparation: one CTA per (padded) gene row of Z -------------------------------------------------
+__global__ void __launch_bounds__(128)
+z_prepare_i8_kernel(const double* __restrict__ Z, int64_t n, int64_t ldk, int64_t ldkb, int64_t rows_pad,
+                    int8_t* __restrict__ planes, double* __restrict__ zscale) {
+  __shared__ double red[4];
+  const int64_t i = blockIdx.x;
+  const int64_t plane_stride = rows_pad * ldkb;
+  int8_t* dst = planes + i * ldkb;
+  double mx = 0.0;
+  if (i < n)
+    for (int64_t k = threadIdx.x; k < ldk; k += 128) mx = fmax(mx, fabs(Z[i * ldk + k]));
+  for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = fmax(fmax(red[0], red[1]), fmax(red[2], red[3]));
+  int ex = 0;
+  if (mx > 0.0) frexp(mx, &ex);  // mx = f 2^ex, f in [0.5, 1)
+  if (ex < -900) ex = -900;
+  const double up = ldexp(1.0, kZBits - ex);  // |z| up <= 2^46, exact scaling
+  if (threadIdx.x == 0) zscale[i] = (i < n && mx > 0.0) ? ldexp(1.0, ex - kZBits) : 0.0;
+  for (int64_t k4 = (int64_t)threadIdx.x * 4; k4 < ldkb; k4 += 128 * 4) {
+    uint32_t packed[kZS];
+#pragma unroll
+    for (int p = 0; p < kZS; ++p) packed[p] = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int64_t k = k4 + e;
+      long long q = 0;
+      if (i < n && k < ldk) q = __double2ll_rn(Z[i * ldk + k] * up);
+#pragma unroll
+      for (int p = 0; p < kZS; ++p) {
+        const long long d = ((q + 128) & 255) - 128;  // balanced digit in [-128, 127]
+        q = (q - d) >> 8;
+        packed[p] |= ((uint32_t)(d & 255)) << (8 * e);
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < kZS; ++p) *reinterpret_cast<uint32_t*>(dst + p * plane_stride + k4) = packed[p];
+  }
+}
+
+// s ** e, the multiplication order of int_pow4 (bitwise the same adjacency as the DMMA route)
+__device__ __forceinline__ double int_pow1(double s, int e) {
+  double r = 1.0;
+#pragma unroll 1
+  while (true) {
+    if (e & 1) r *= s;
+    e >>= 1;
+    if (!e) break;
+    s *= s;
+  }
+  return r;
+}
+
+// the tile walk every role of the CTA repeats: column-major over the CT x RT grid (or its upper triangle)
+struct TileWalk {
+  int64_t t, t1, jt, it, RT;
+  bool sym;
+  __device__ __forceinline__ void init(const SweepParams& prm) {
+    int64_t t0;
+    sweep_range(prm.T, gridDim.x, blockIdx.x, t0, t1);
+    t = t0;
+    sym = prm.symmetric != 0;
+    RT = prm.RT;
+    if (t0 >= t1) return;
+    if (sym) {
+      jt = sym_col_of(t0);
+      it = t0 - sym_offset(jt);
+    } else {
+      jt = t0 / RT;
+      it = t0 - jt * RT;
+    }
+  }
+  __device__ __forceinline__ bool valid() const { return t < t1; }
+  __device__ __forceinline__ void next() {
+    ++t;
+    ++it;
+    if (it >= (sym ? (jt >> 1) + 1 : RT)) { ++jt; it = 0; }
+  }
+};
+
+__global__ void __launch_bounds__(kCThreads, 1)
+sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
+                const __grid_constant__ SweepParams prm, const int nkb) {
+  constexpr int kBN = kSweepBN, kBM = kSweepBM;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  double* park = reinterpret_cast<double*>(smem + kCStages * kCStageBytes);
+  CorrBars* bars = reinterpret_cast<CorrBars*>(park + kParkDoubles);
+  __shared__ uint8_t bad_col[kBN], bad_row[kBM];
+  __shared__ double col_scale[kBN];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 5 && lane == 0) {
+    for (int s = 0; s < kCStages; ++s) {
+      tc::mbar_init(&bars->full[s], 1);
+      tc::mbar_init(&bars->empty[s], 1);
+    }
+    tc::mbar_init(&bars->acc_full, 1);
+    tc::mbar_init(&bars->acc_empty, 4);  // lane 0 of every epilogue warp
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(&bars->tmem_base)),
+                 "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc::fence_before();
+  __syncthreads();
+  tc::fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  const int64_t n = prm.n;
+
+  if (warp == 4) {
+    // ================================= TMA producer =================================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapB) : "memory");
+      TileWalk w;
+      w.init(prm);
+      uint32_t step = 0;
+      for (; w.valid(); w.next()) {
+        const int i0 = (int)(w.it * kBM), j0 = (int)(prm.col0 + w.jt * kBN);
+        for (int kb = 0; kb < nkb; ++kb, ++step) {
+          const int stage = step & 1;
+          tc::mbar_wait(&bars->empty[stage], ((step >> 1) & 1) ^ 1);
+          uint8_t* a_dst = smem + stage * kCStageBytes;
+          tc::mbar_expect_tx(&bars->full[stage], kCStageBytes);
+          tc::tma_load_3d(a_dst, &tmapA, &bars->full[stage], kb * kCKB, i0, 0);
+          tc::tma_load_3d(a_dst + kCAStage, &tmapB, &bars->full[stage], kb * kCKB, j0, 0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ================================== MMA issuer ==================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_i8_idesc(kBM, kBN);
+      TileWalk w;
+      w.init(prm);
+      uint32_t step = 0, tile_no = 0;
+      for (; w.valid(); w.next(), ++tile_no) {
+        tc::mbar_wait(&bars->acc_empty, (tile_no & 1) ^ 1);  // the epilogue has drained the previous tile
+        tc::fence_after();
+        for (int kb = 0; kb < nkb; ++kb, ++step) {
+          const int stage = step & 1;
+          tc::mbar_wait(&bars->full[stage], (step >> 1) & 1);
+          tc::fence_after();
+          const uint32_t a_addr = tc::smem_u32(smem + stage * kCStageBytes);
+          const uint32_t b_addr = a_addr + kCAStage;
+          uint32_t used = kb == 0 ? 0u : 0xffffffffu;  // accumulators that already hold a product of this tile
+#pragma unroll
+          for (int s = kZS - 1; s >= 0; --s) {
+#pragma unroll
+            for (int t = kZS - 1; t >= 0; --t) {
+              if (s + t < kZWmin) continue;
+              const int a = s + t - kZWmin;
+              const uint64_t adesc = tc::make_sw64_desc(a_addr + s * (kBM * kCKB));
+              const uint64_t bdesc = tc::make_sw64_desc(b_addr + t * (kBN * kCKB));
+              const uint32_t tmem_d = tmem_base + (uint32_t)(a * kBN);
+#pragma unroll
+              for (int kk = 0; kk < kCKB / 32; ++kk) {
+                // K advance inside the 64-byte swizzle atom: +32 bytes on the start address (>> 4 = 2)
+                tc::mma_i8(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
+                           ((used >> a) & 1u) | (uint32_t)kk);
+              }
+              used |= 1u << a;
+            }
+          }
+          tc::commit(&bars->empty[stage]);  // frees the stage when these MMAs retire
+        }
+        tc::commit(&bars->acc_full);  // all six accumulators complete -> epilogue
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================= epilogue (warps 0-3) =============================
+    const int wm = warp >> 1, wn = warp & 1;
+    const int P = prm.P;
+    const int64_t jend = prm.col0 + prm.ncols;
+    double adj_power = prm.adj_power;
+    int adj_ipower = prm.adj_ipower;
+    if (prm.d_adj_power != nullptr) {
+      adj_power = *prm.d_adj_power;
+      adj_ipower = small_int_power(adj_power);
+    }
+    const bool adj_mode = P == 0;
+    TileWalk w;
+    w.init(prm);
+    const int64_t jt_first = w.valid() ? w.jt : 0;
+    int64_t cur_jt = -1;
+    uint32_t tile_no = 0;
+    double kcol[kSweepMaxP];
+#pragma unroll
+    for (int p = 0; p < kSweepMaxP; ++p) kcol[p] = 0.0;
+    const int col = wn * 32 + lane;
+
+    auto flush = [&](int64_t jt_done) {
+      // column sums of a finished column tile -> this CTA's slot; the two warps that share a column add up
+      // in a fixed order (deterministic, no atomics)
+      double* dst = prm.partial + ((int64_t)blockIdx.x * prm.max_seg + (jt_done - jt_first)) * P * kBN;
+      if (wm == 0) {
+#pragma unroll
+        for (int p = 0; p < kSweepMaxP; ++p)
+          if (p < P) dst[p * kBN + col] = kcol[p];
+      }
+      tc::epi_barrier();
+      if (wm == 1) {
+#pragma unroll
+        for (int p = 0; p < kSweepMaxP; ++p)
+          if (p < P) dst[p * kBN + col] += kcol[p];
+      }
+#pragma unroll
+      for (int p = 0; p < kSweepMaxP; ++p) kcol[p] = 0.0;
+    };
+
+    for (; w.valid(); w.next(), ++tile_no) {
+      const int64_t jt = w.jt, it = w.it, t = w.t;
+      const int64_t j0 = prm.col0 + jt * kBN, i0 = it * kBM;
+      const bool two_pass = w.sym && it < (jt >> 1);  // strictly above the diagonal block
+      tc::epi_barrier();  // every warp is done with the parked tile, bad_row, col_scale of the previous tile
+      if (jt != cur_jt) {
+        if (cur_jt >= 0 && P > 0) flush(cur_jt);
+        if (threadIdx.x < kBN) {
+          const int64_t j = j0 + threadIdx.x;
+          bad_col[threadIdx.x] = (j < jend) ? prm.bad[j] : 1;
+          // 2^40 = 256^5: the weight of the lowest accumulator
+          col_scale[threadIdx.x] = (j < n) ? prm.zscale[j] * 1099511627776.0 : 0.0;
+        }
+        cur_jt = jt;
+      }
+      {
+        const int64_t i = i0 + threadIdx.x;  // 128 threads = 128 rows
+        bad_row[threadIdx.x] = (i < n) ? prm.bad[i] : 1;
+      }
+      tc::epi_barrier();
+      // ---- drain: thread <-> row (TMEM lane), the six accumulators combined in float64 ----
+      {
+        const int row = threadIdx.x;
+        const int64_t gi = i0 + row;
+        const double si = gi < n ? prm.zscale[gi] : 0.0;
+        tc::mbar_wait(&bars->acc_full, tile_no & 1);
+        tc::fence_after();
+#pragma unroll 1
+        for (int c = 0; c < kBN / 16; ++c) {
+          uint32_t r[kZAcc][16];
+#pragma unroll
+          for (int a = 0; a < kZAcc; ++a)
+            tc::ld_32x32_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * kBN + c * 16), r[a]);
+          tc::ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            double v = (double)(int)r[kZAcc - 1][j];
+#pragma unroll
+            for (int a = kZAcc - 2; a >= 0; --a) v = v * 256.0 + (double)(int)r[a][j];
+            park[row * kParkPitch + c * 16 + j] = v * (si * col_scale[c * 16 + j]);  // powers of two: exact
+          }
+        }
+        tc::fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bars->acc_empty);  // TMEM is free: the next tile's MMAs may start
+      }
+      tc::epi_barrier();  // the whole tile is parked
+
+      const int64_t gj = j0 + col;
+      const bool cbad = bad_col[col];
+      const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+      double* my = park + (wm * 64) * kParkPitch + wn * 32;  // this warp's 64 x 32 sub-tile
+
+      // similarity and chain start of one element: wgcna.py:884-897, NaN skipped by nansum (:915); with prm.sim the
+      // similarity (sweep) or s ** power (adjacency mode, wgcna.py:1111) is written the way WGCNA.adjacency forms
+      // it: diagonal not forced, NaN rows and columns kept
+      auto load = [&](int r, double& sv, double& c0) {
+        const int row = wm * 64 + r;
+        const int64_t gi = i0 + row;
+        double c = my[r * kParkPitch + lane];
+        c = fmin(1.0, fmax(-1.0, c));  // np.corrcoef clips to [-1, 1]
+        sv = net_transform(c, prm.net_type);
+        c0 = 1.0;
+        const bool nan_pair = cbad || bad_row[row];
+        if (prm.sim != nullptr) {
+          double s_out = sv;
+          if (adj_mode) s_out = adj_ipower > 0 ? int_pow1(sv, adj_ipower) : pow(sv, adj_power);
+          if (nan_pair) s_out = qnan;
+          if (prm.sim_transposed) my[r * kParkPitch + lane] = s_out;  // stored by the transposed pass below
+          else if (gi < n && gj < jend) prm.sim[gi * n + gj] = s_out;
+        }
+        if (gi == gj) sv = 1.0;  // wgcna.py:897 (even for a NaN gene)
+        else if (nan_pair) { sv = 0.0; c0 = 0.0; }
+        if (gi >= n) { sv = 0.0; c0 = 0.0; }
+      };
+
+#pragma unroll 1
+      for (int r0 = 0; r0 < 64; r0 += 8) {
+        double s1[8], s2[8], cur[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          load(r0 + u, s1[u], cur[u]);
+          s2[u] = s1[u] * s1[u];
+        }
+#pragma unroll
+        for (int p = 0; p < kSweepMaxP; ++p) {
+          if (p < P) {  // wgcna.py:914  corxCur = corxPrev * corx ** step
+            const bool one = prm.istep[p] == 1;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) cur[u] *= one ? s1[u] : s2[u];
+            kcol[p] += ((cur[0] + cur[1]) + (cur[2] + cur[3])) + ((cur[4] + cur[5]) + (cur[6] + cur[7]));
+          }
+        }
+      }
+      if (two_pass) {
+        // rows lane and lane + 32 of the warp's 64, its 32 columns four at a time: row sums for the genes of the
+        // tile's rows (their column tiles never visit these rows), and the mirrored half of the output
+        double kr[2][kSweepMaxP];
+#pragma unroll
+        for (int p = 0; p < kSweepMaxP; ++p) kr[0][p] = kr[1][p] = 0.0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 32; c0 += 4) {
+          double s1[8], s2[8], cur[8];
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int r = h * 32 + lane, row = wm * 64 + r, colx = wn * 32 + c0 + u;
+              const int64_t gi = i0 + row, gjx = j0 + colx;
+              double c = my[r * kParkPitch + c0 + u];
+              c = fmin(1.0, fmax(-1.0, c));
+              double sv = net_transform(c, prm.net_type), c0v = 1.0;
+              const bool nan_pair = bad_col[colx] || bad_row[row];
+              const bool inside = gi < n && gjx < jend;
+              if (prm.sim != nullptr && inside) {
+                double s_out = sv;
+                if (adj_mode) s_out = adj_ipower > 0 ? int_pow1(sv, adj_ipower) : pow(sv, adj_power);
+                prm.sim[gjx * n + gi] = nan_pair ? qnan : s_out;
+              }
+              if (nan_pair || !inside) { sv = 0.0; c0v = 0.0; }
+              s1[h * 4 + u] = sv;
+              s2[h * 4 + u] = sv * sv;
+              cur[h * 4 + u] = c0v;
+            }
+#pragma unroll
+          for (int p = 0; p < kSweepMaxP; ++p) {
+            if (p < P) {
+              const bool one = prm.istep[p] == 1;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) cur[e] *= one ? s1[e] : s2[e];
+              kr[0][p] += (cur[0] + cur[1]) + (cur[2] + cur[3]);
+              kr[1][p] += (cur[4] + cur[5]) + (cur[6] + cur[7]);
+            }
+          }
+        }
+        if (P > 0) {
+          // the two warps that share rows add up through the (now free) parking space: [wn][p][row]
+          tc::epi_barrier();
+#pragma unroll
+          for (int p = 0; p < kSweepMaxP; ++p)
+            if (p < P) {
+              park[(wn * P + p) * kBM + wm * 64 + lane] = kr[0][p];
+              park[(wn * P + p) * kBM + wm * 64 + 32 + lane] = kr[1][p];
+            }
+          tc::epi_barrier();
+          const int row = threadIdx.x;
+          double* dst = prm.rowpart + t * P * kBM;
+          for (int p = 0; p < P; ++p) dst[p * kBM + row] = park[p * kBM + row] + park[(P + p) * kBM + row];
+        }
+      }
+      if (prm.sim != nullptr && prm.sim_transposed) {  // lane <-> row of the sub-tile: 256-byte row segments
+        __syncwarp();
+#pragma unroll 1
+        for (int c = 0; c < 32; ++c) {
+          const int64_t gjc = j0 + wn * 32 + c;
+          if (gjc >= jend) break;  // warp-uniform
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int r = h * 32 + lane;
+            const int64_t gi = i0 + wm * 64 + r;
+            if (gi < n) prm.sim[(gjc - prm.col0) * n + gi] = my[r * kParkPitch + c];
+          }
+        }
+      }
+    }
+    if (cur_jt >= 0 && P > 0) {
+      tc::epi_barrier();
+      flush(cur_jt);
+    }
+  }
+  tc::fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc::fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn corr_encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      sym = nullptr;
+    return (EncodeTiledFn)sym;
+  }();
+  return fn;
+}
+
+static std::atomic<int> g_corr_precision{-1};  // -1: environment / default
+
+bool corr_i8_enabled(int64_t m, int64_t n) {
+  int prec = g_corr_precision.load();
+  if (prec < 0) {
+    const char* e = getenv("B200WGCNA_CORR_PRECISION");
+    prec = (e && (e[0] == 'f' || e[0] == 'F')) ? B200W_PREC_F64 : B200W_PREC_I8;
+  }
+  // per pair and accumulator |sum| <= K * 2^14 * (pairs of one weight <= 6) must stay below 2^31
+  const int64_t ldkb = round_up(m, kCKB);
+  return prec != B200W_PREC_F64 && ldkb * 6 * 16384 < 2147483647LL && n >= 1;
+}
+
+// One launch of the tcgen05 sweep / adjacency engine.  prm is filled by the caller as for corr.cu's sweep_kernel
+// (partial / rowpart / T / max_seg / symmetric ...); planes and scales are made here, stream ordered.
+int sweep_i8_launch(SweepParams prm, int64_t m, int64_t CT, int P, int G, int device, cudaStream_t st) {
+  EncodeTiledFn encode = corr_encode_tiled();
+  if (!encode) return fail(B200W_E_CUDA, "corr_i8: cuTensorMapEncodeTiled not available from the driver");
+  const int64_t n = prm.n;
+  const int64_t ldkb = round_up(m, kCKB), rows_pad = round_up(n, 128);
+  if (rows_pad > 0x7fffffff || ldkb > 0x7fffffff) return fail(B200W_E_UNSUPPORTED, "corr_i8: problem too large");
+  Scratch planes, zscale;
+  B200W_CUDA(planes.alloc((size_t)kZS * rows_pad * ldkb, st));
+  B200W_CUDA(zscale.alloc((size_t)rows_pad * sizeof(double), st));
+  z_prepare_i8_kernel<<<(unsigned)rows_pad, 128, 0, st>>>(prm.Z, n, prm.ldk, ldkb, rows_pad, planes.as<int8_t>(),
+                                                           zscale.as<double>());
+  B200W_LAUNCHED();
+  prm.zscale = zscale.as<double>();
+
+  CUtensorMap tmapA, tmapB;
+  const cuuint64_t gdim[3] = {(cuuint64_t)ldkb, (cuuint64_t)rows_pad, (cuuint64_t)kZS};
+  const cuuint64_t gstride[2] = {(cuuint64_t)ldkb, (cuuint64_t)ldkb * (cuuint64_t)rows_pad};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  const cuuint32_t boxA[3] = {(cuuint32_t)kCKB, (cuuint32_t)kSweepBM, (cuuint32_t)kZS};
+  const cuuint32_t boxB[3] = {(cuuint32_t)kCKB, (cuuint32_t)kSweepBN, (cuuint32_t)kZS};
+  CUresult cr = encode(&tmapA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, planes.p, gdim, gstride, boxA, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr == CUDA_SUCCESS)
+    cr = encode(&tmapB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, planes.p, gdim, gstride, boxB, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return fail(B200W_E_CUDA, "corr_i8: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+  B200W_CUDA(cudaFuncSetAttribute(sweep_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCorrSmem));
+  sweep_i8_kernel<<<G, kCThreads, kCorrSmem, st>>>(tmapA, tmapB, prm, (int)(ldkb / kCKB));
+  B200W_LAUNCHED();
+  (void)CT;
+  (void)P;
+  (void)device;
+  return 0;
+}
+
+}  // namespace b200w
+
+extern "C" int b200w_set_correlation_precision(int precision) {
+  if (precision != B200W_PREC_AUTO && precision != B200W_PREC_F64 && precision != B200W_PREC_I8)
+    return b200w::fail(B200W_E_INVALID, "set_correlation_precision: B200W_PREC_AUTO, _F64 or _I8");
+  b200w::g_corr_precision.store(precision == B200W_PREC_AUTO ? -1 : precision);
+  return 0;
+}

@@ -57,15 +57,30 @@ class SftTable:
 
             self._event.synchronize()
             h_stats, h_buck, h_fit, h_power, _ = self._bufs
-            self.device_fit = h_fit.numpy().copy()
-            self.device_power = float(h_power[0])
+            self._device_fit = h_fit.numpy().copy()
+            self._device_power = float(h_power[0])
             vals = W.fit_table_from_stats(h_stats.numpy(), h_buck.numpy(), self.n, self.nBreaks)
             self._cols = dict(zip(self.COLUMNS, vals))
             r2, mean = self._cols["SFT.R.sq"], self._cols["mean(k)"]
             with np.errstate(invalid="ignore"):
                 ind = (r2 > self.RsquaredCut) & (mean <= self.MeanCut)  # wgcna.py:945
-            self.host_power = self.powers[ind].min() if ind.any() else self.powers[np.argsort(r2)[-1]]
+            self._host_power = self.powers[ind].min() if ind.any() else self.powers[np.argsort(r2)[-1]]
         return self._cols
+
+    @property
+    def device_fit(self):
+        self._evaluate()
+        return self._device_fit
+
+    @property
+    def device_power(self):
+        self._evaluate()
+        return self._device_power
+
+    @property
+    def host_power(self):
+        self._evaluate()
+        return self._host_power
 
     def __getitem__(self, name):
         return self._evaluate()[name]
@@ -445,6 +460,15 @@ class DeviceNetwork:
         return T
 
 
+_NET_CACHE = {}
+
+
+def release_workspace():
+    """Drop the device workspace ``network_blocks`` keeps between calls."""
+    _NET_CACHE.clear()
+    torch.cuda.empty_cache()
+
+
 def network_blocks(datExpr, powerVector=None, networkType="unsigned", TOMType="signed", TOMDenom="min",
                    RsquaredCut=0.9, MeanCut=100, nBreaks=10, power=None, device=None, precision="auto",
                    out_mode: int = L.OUT_TOM, return_adjacency: bool = False):
@@ -467,10 +491,20 @@ def network_blocks(datExpr, powerVector=None, networkType="unsigned", TOMType="s
     dev = L.default_device() if device is None else int(device)
     torch.cuda.set_device(dev)
     m, n = X.shape
-    Xd = torch.empty((m, n), dtype=torch.float64, device=torch.device("cuda", dev))
-    st = torch.cuda.current_stream(Xd.device).cuda_stream
-    L.check(lib.b200w_dev_upload(Xd.data_ptr(), L.hptr(X), X.nbytes, dev, st))
-    net = DeviceNetwork(Xd, device=dev, networkType=networkType, precision=precision)
+    # the device workspace (and, under torchrun, the peer mappings: IPC handle exchange + cudaIpcOpenMemHandle
+    # cost hundreds of ms) is kept between calls of the same shape, like the DevCache of the C entry points
+    dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
+    key = (dev, m, n, networkType, precision, torch.distributed.get_world_size() if dist_on else 1)
+    net = _NET_CACHE.get(key)
+    if net is None:
+        _NET_CACHE.clear()  # one workspace at a time: these are tens of GB
+        net = DeviceNetwork(torch.empty((m, n), dtype=torch.float64, device=torch.device("cuda", dev)), device=dev,
+                            networkType=networkType, precision=precision)
+        _NET_CACHE[key] = net
+    st = torch.cuda.current_stream(net.dev).cuda_stream
+    L.check(lib.b200w_dev_upload(net.X.data_ptr(), L.hptr(X), X.nbytes, dev, st))
+    net._standardized = False
+    net._sim_in_A = False
     sft = None
     picked = power is None
     if picked:

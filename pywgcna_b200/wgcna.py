@@ -52,6 +52,12 @@ PRECISION = os.environ.get("B200WGCNA_PRECISION", "auto")
 _PREC = {"auto": L.PREC_AUTO, "f64": L.PREC_F64, "i8": L.PREC_I8, "i8-fast": L.PREC_I8_FAST}
 
 
+def set_correlation_precision(precision: str = "auto"):
+    """Arithmetic of the correlation product behind ``pickSoftThreshold`` / ``adjacency`` (process wide):
+    ``"i8"`` (= ``"auto"``) the tcgen05 int8 digit-plane engine, ``"f64"`` the FP64 DMMA engine."""
+    L.check(L.load().b200w_set_correlation_precision({"auto": L.PREC_AUTO, "f64": L.PREC_F64, "i8": L.PREC_I8}[precision]))
+
+
 def _say(*a, **k):
     if VERBOSE:
         print(*a, **k)

@@ -15,6 +15,15 @@ from oracle import restated as O
 from pywgcna_b200 import _lib
 from pywgcna_b200.synth import make_expression
 
+
+@pytest.fixture(autouse=True, params=["i8", "f64"])
+def corr_engine(request):
+    """Every test of this module runs on both correlation engines: tcgen05 int8 digit planes (corr_i8.cu, the
+    default) and FP64 DMMA (corr.cu)."""
+    bw.set_correlation_precision(request.param)
+    yield request.param
+    bw.set_correlation_precision("auto")
+
 pytestmark = pytest.mark.gpu
 
 NETS = ["unsigned", "signed", "signed hybrid"]

@@ -66,6 +66,39 @@ def test_tom_from_adj_symmetric_matches_tomsimilarity(gpu):
 
 
 # ------------------------------------------------------------------------------------------------
+# the tcgen05 correlation engine (corr_i8.cu) against np.corrcoef itself
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m,n", [(200, 1500), (37, 131), (500, 2049), (5000, 700), (3, 300)])
+def test_int8_correlation_matches_corrcoef(gpu, m, n):
+    """unsigned adjacency with power 1 is |np.corrcoef| (wgcna.py:1097-1111): the int8 digit-plane product is
+    within 1e-12 of numpy float64 (north-star tolerance 1e-6), bitwise symmetric, and both engines agree."""
+    X = make_expression(m, n, F=5, seed=m * 1000 + n)
+    X[:, 1] = X[:, 0]          # duplicate genes: cor = 1 exactly (clipped)
+    X[:, 2] = -3.0 * X[:, 0]   # cor = -1
+    X[:, 3] *= 1e-6            # tiny scale: the per-gene exponent carries it
+    X[0, 4] += 1e3             # one dominant sample: the largest digit range in one entry
+    ref = np.abs(np.corrcoef(X, rowvar=False))
+    out = {}
+    for eng in ("i8", "f64"):
+        bw.set_correlation_precision(eng)
+        try:
+            out[eng] = bw.adjacency(pd.DataFrame(X), adjacencyType="unsigned", power=1)
+        finally:
+            bw.set_correlation_precision("auto")
+        assert np.array_equal(out[eng], out[eng].T)
+        np.testing.assert_allclose(out[eng], ref, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(out["i8"], out["f64"], rtol=0, atol=1e-12)
+    # signed network, non-integer power: the pow() branch of the fused epilogue
+    for eng in ("i8", "f64"):
+        bw.set_correlation_precision(eng)
+        try:
+            A = bw.adjacency(pd.DataFrame(X), adjacencyType="signed", power=2.5)
+        finally:
+            bw.set_correlation_precision("auto")
+        np.testing.assert_allclose(A, ((1 + np.corrcoef(X, rowvar=False)) / 2) ** 2.5, rtol=0, atol=1e-11)
+
+
+# ------------------------------------------------------------------------------------------------
 # full-size C2: the reference's own soft-threshold table and selected power (wgcna.py:924-953)
 # ------------------------------------------------------------------------------------------------
 def test_c2_fullsize_soft_threshold_table(gpu, golden_dir):
@@ -80,7 +113,8 @@ def test_c2_fullsize_soft_threshold_table(gpu, golden_dir):
     got, ref = sft.to_numpy(dtype=float), g["sft"]
     assert np.array_equal(got[:, 0], ref[:, 0])
     np.testing.assert_allclose(got[:, 1:4], ref[:, 1:4], rtol=0, atol=1e-9)   # R^2, slope, truncated R^2
-    np.testing.assert_allclose(got[:, 4:], ref[:, 4:], rtol=1e-12, atol=0)    # mean, median, max of k
+    # mean, median, max of k (k = sum - 1: the absolute error of a sum of 20 000 terms stays when k is tiny)
+    np.testing.assert_allclose(got[:, 4:], ref[:, 4:], rtol=1e-11, atol=1e-12)
     # sampled rows of the reference's adjacency and TOM at that power
     rows = g["rows"]
     A = bw.adjacency(df, adjacencyType=net, power=p)
