@@ -762,7 +762,7 @@ static int adjacency_impl(const double* dZ, const uint8_t* d_bad, int64_t m, int
   if (net_type < 0 || net_type > 2) return fail(B200W_E_INVALID, "adjacency: bad network type");
   if (int e = ensure_device(device)) return e;
   cudaStream_t st = (cudaStream_t)stream;
-  if (corr_i8_enabled(m, n) && row0 % kSweepBN == 0) {
+  if (corr_i8_enabled(m, n)) {
     // tcgen05 engine: the sweep's tile walk without a chain (P = 0), the output written as s ** power
     int sms = 0;
     B200W_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));

@@ -6,11 +6,14 @@
 // exactly in integers: every standardised gene (a unit-norm row of Z, |z| <= 1) is scaled by 2^(46 - e_i), e_i
 // the binary exponent of its largest magnitude, rounded to a 46-bit integer and cut into S = 6 balanced base-256
 // digits (int8 planes).  cor_ij = 2^(e_i + e_j - 92) sum_{s,t} 256^(s+t) sum_k d^s_ik d^t_jk ; each inner sum is an
-// s8 x s8 GEMM accumulated exactly in int32.  The 21 digit pairs of weight w = s + t >= 5 are kept (the dropped
-// ones are below 2^-40 of a unit correlation); the pairs of one weight share one TMEM accumulator, so a tile
-// holds SIX 128 x 64 accumulators (384 TMEM columns) and the epilogue combines them once:
-// ((((a10 * 256 + a9) * 256 + a8) ... ) * 256 + a5) * 2^40 * 2^(e_i + e_j - 92), every factor a power of two, so
-// cor_ij and cor_ji are bitwise equal and do not depend on the tile schedule or on the number of GPUs.
+// s8 x s8 GEMM accumulated exactly in int32.  The 21 digit pairs of weight w = s + t >= 5 are kept, plus the
+// pair (2, 2) of weight 4: for strongly correlated genes (and on the diagonal) the digits of equal planes are
+// themselves correlated, so that one dropped product is a coherent sum ~ K * 5e3 * 256^4 (measured: 2e-13 at
+// K = 200, 2e-11 for a gene with one dominant sample), while the dropped pairs of unequal planes stay random
+// (~1e-14).  The pairs of one weight share one TMEM accumulator, so a tile holds SEVEN 128 x 64 accumulators
+// (448 TMEM columns) and the epilogue combines them once:
+// (((((a10 * 256 + a9) * 256 + a8) ... ) * 256 + a5) * 256 + a4) * 2^32 * 2^(e_i + e_j - 92), every factor a power
+// of two, so cor_ij and cor_ji are bitwise equal and do not depend on the tile schedule or on the number of GPUs.
 // Measured against np.corrcoef: <= 2e-13 (tests/test_gpu_round2.py).
 //
 // Kernel (persistent, one CTA per SM, 192 threads):
@@ -18,7 +21,7 @@
 //              {64 B, 64 rows, 6 planes} of the column genes (SWIZZLE_64B), 2-stage ring of 72 KB -- all 21
 //              pair products of a K step are issued from the same staged bytes (36 B/clk of L2 traffic per SM
 //              instead of 125 with a stage per pair)
-//   warp 5     TMEM allocation (512 columns) and MMA issue: 21 pairs x 2 tcgen05.mma M128 N64 K32 per stage
+//   warp 5     TMEM allocation (512 columns) and MMA issue: 22 pairs x 2 tcgen05.mma M128 N64 K32 per stage
 //   warps 0-3  epilogue: drain the six accumulators (tcgen05.ld 32x32b.x16), combine, park the float64 tile in
 //              shared memory, release TMEM (the MMAs of the next tile run under the rest), then the epilogue of
 //              corr.cu's sweep_kernel on the parked tile: lane <-> column, power chain with the P column sums in
@@ -33,7 +36,8 @@ namespace b200w {
 constexpr int kZS = 6;                              // digit planes of Z
 constexpr int kZBits = 8 * kZS - 2;                 // 46
 constexpr int kZWmin = 5;                           // lowest digit-pair weight kept
-constexpr int kZAcc = 2 * (kZS - 1) - kZWmin + 1;   // 6 accumulators, weights 5 .. 10
+constexpr int kZAccHi = 2 * (kZS - 1) - kZWmin + 1;  // 6 accumulators, weights 5 .. 10
+constexpr int kZAcc = kZAccHi + 1;                  // + one for the pair (2, 2) of weight 4, see below
 constexpr int kCKB = 64;                            // K bytes per stage
 constexpr int kCStages = 2;
 constexpr int kCThreads = 192;                      // warps 0-3 epilogue, 4 TMA, 5 MMA
@@ -296,8 +300,8 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
           for (int s = kZS - 1; s >= 0; --s) {
 #pragma unroll
             for (int t = kZS - 1; t >= 0; --t) {
-              if (s + t < kZWmin) continue;
-              const int a = s + t - kZWmin;
+              if (s + t < kZWmin && !(s == 2 && t == 2)) continue;
+              const int a = s + t >= kZWmin ? s + t - kZWmin : kZAccHi;  // (2, 2) has an accumulator of its own
               const uint64_t adesc = tc::make_sw64_desc(a_addr + s * (kBM * kCKB));
               const uint64_t bdesc = tc::make_sw64_desc(b_addr + t * (kBN * kCKB));
               const uint32_t tmem_d = tmem_base + (uint32_t)(a * kBN);
@@ -367,8 +371,8 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
         if (threadIdx.x < kBN) {
           const int64_t j = j0 + threadIdx.x;
           bad_col[threadIdx.x] = (j < jend) ? prm.bad[j] : 1;
-          // 2^40 = 256^5: the weight of the lowest accumulator
-          col_scale[threadIdx.x] = (j < n) ? prm.zscale[j] * 1099511627776.0 : 0.0;
+          // 2^32 = 256^4: the weight of the lowest accumulator
+          col_scale[threadIdx.x] = (j < n) ? prm.zscale[j] * 4294967296.0 : 0.0;
         }
         cur_jt = jt;
       }
@@ -393,9 +397,10 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
           tc::ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            double v = (double)(int)r[kZAcc - 1][j];
+            double v = (double)(int)r[kZAccHi - 1][j];
 #pragma unroll
-            for (int a = kZAcc - 2; a >= 0; --a) v = v * 256.0 + (double)(int)r[a][j];
+            for (int a = kZAccHi - 2; a >= 0; --a) v = v * 256.0 + (double)(int)r[a][j];
+            v = v * 256.0 + (double)(int)r[kZAccHi][j];  // weight 4
             park[row * kParkPitch + c * 16 + j] = v * (si * col_scale[c * 16 + j]);  // powers of two: exact
           }
         }
@@ -560,7 +565,7 @@ bool corr_i8_enabled(int64_t m, int64_t n) {
     const char* e = getenv("B200WGCNA_CORR_PRECISION");
     prec = (e && (e[0] == 'f' || e[0] == 'F')) ? B200W_PREC_F64 : B200W_PREC_I8;
   }
-  // per pair and accumulator |sum| <= K * 2^14 * (pairs of one weight <= 6) must stay below 2^31
+  // per accumulator |sum| <= K * 2^14 * (pairs of one weight <= 6) must stay below 2^31
   const int64_t ldkb = round_up(m, kCKB);
   return prec != B200W_PREC_F64 && ldkb * 6 * 16384 < 2147483647LL && n >= 1;
 }

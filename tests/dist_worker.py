@@ -75,6 +75,13 @@ def main():
                        "tom_vs_oracle": float(np.abs(Td - T_ref).max()),
                        "adj_vs_oracle": float(np.nanmax(np.abs(Ad - A_ref))),
                        "table_power": float(tab.host_power)}
+                if not rec["adj_bitwise"]:
+                    A1n = A1.cpu().numpy()
+                    diff = ~((Ad == A1n) | (np.isnan(Ad) & np.isnan(A1n)))
+                    ii, jj = np.nonzero(diff)
+                    rec["adj_ndiff"] = int(diff.sum())
+                    rec["adj_first_diffs"] = [(int(a), int(b), float(Ad[a, b]), float(A1n[a, b]))
+                                              for a, b in list(zip(ii, jj))[:6]]
                 good = (rec["power_equal"] and rec["k_max_abs"] <= 1e-9 and rec["adj_bitwise"] and rec["tom_bitwise"]
                         and rec["tom_vs_oracle"] <= 1e-10 and rec["adj_vs_oracle"] <= 1e-11
                         and rec["table_power"] == p_dist)
