@@ -142,6 +142,18 @@ int b200w_dev_cross_correlation(const double* dZx, const uint8_t* d_badx, int64_
                                 const uint8_t* d_bady, int64_t M, int64_t m, double* dC, int device,
                                 void* stream);
 
+/* Average-linkage clustering of the genes, the call that follows the TOM in findModules:
+ * scipy.cluster.hierarchy.linkage(squareform(dissTOM), method="average") (wgcna.py:326-328), with scipy's exact
+ * result -- nearest-neighbour-chain merge order including its tie rules, Lance-Williams heights, stable sort by
+ * height, union-find labels (scipy/cluster/_hierarchy.pyx, scipy==1.14.0 pinned by the reference).
+ *   y_condensed  n (n - 1) / 2 distances in squareform order;  Z_out  (n - 1) x 4 linkage matrix.
+ * b200w_dev_linkage_average works on the n x n square form in HBM (symmetric, destroyed) and leaves the merges
+ * in chain order (x, y, height, size) in d_Zraw; b200w_linkage_finish (host) sorts and labels them in place. */
+int b200w_linkage_average(const double* y_condensed, int64_t n, double* Z_out, int device);
+int b200w_dev_linkage_average(double* d_D, int64_t n, double* d_Zraw, int device, void* stream);
+int b200w_dev_condensed_to_square(const double* d_y, int64_t n, double* d_D, int device, void* stream);
+int b200w_linkage_finish(double* Z, int64_t n);
+
 /* WGCNA.intramodularConnectivity, wgcna.py:3431-3445: diag <- 0, NaN -> 0, per-module
  * within-module row sums.  labels[n] are module ids in [0, nmod); small[nmod] != 0 marks
  * modules with < 3 genes (kWithin = 0, :3436).  out: kTotal[n], kWithin[n]. */

@@ -51,6 +51,10 @@ SIGNATURES = {
     "b200w_network": (_int, [_dp, _i64, _i64, _int, _dbl, _int, _int, _int, _int, _dp, _dp, _int]),
     "b200w_cross_correlation": (_int, [_dp, _i64, _i64, _dp, _i64, _dp, _int]),
     "b200w_dev_cross_correlation": (_int, [_dp, _dp, _i64, _dp, _dp, _i64, _i64, _dp, _int, _dp]),
+    "b200w_linkage_average": (_int, [_dp, _i64, _dp, _int]),
+    "b200w_dev_linkage_average": (_int, [_dp, _i64, _dp, _int, _dp]),
+    "b200w_dev_condensed_to_square": (_int, [_dp, _i64, _dp, _int, _dp]),
+    "b200w_linkage_finish": (_int, [_dp, _i64]),
     "b200w_intramodular": (_int, [_dp, _i64, _dp, _int, _dp, _dp, _dp, _int]),
     "b200w_host_alloc": (C.c_void_p, [_i64]),
     "b200w_host_free": (None, [C.c_void_p]),

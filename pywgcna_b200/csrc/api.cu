@@ -690,6 +690,32 @@ extern "C" int b200w_cross_correlation(const double* X, int64_t m, int64_t n, co
   return 0;
 }
 
+extern "C" int b200w_linkage_average(const double* y_condensed, int64_t n, double* Z_out, int device) {
+  if (!y_condensed || !Z_out || n < 2) return fail(B200W_E_INVALID, "linkage_average: bad args");
+  if (int e = ensure_device(device)) return e;
+  Stream st;
+  B200W_CUDA(st.create());
+  Trace tr("b200w_linkage_average", st.s);
+  DevBuf dY, dD, dZ;
+  HostPin pin;
+  StreamDrain drain{st.s};
+  const size_t cbytes = (size_t)n * (n - 1) / 2 * 8;
+  pin.pin(y_condensed, cbytes);
+  B200W_CUDA(dY.alloc(cbytes));
+  B200W_CUDA(dD.alloc((size_t)n * n * 8));
+  B200W_CUDA(dZ.alloc((size_t)(n - 1) * 4 * 8));
+  B200W_CUDA(cudaMemcpyAsync(dY.p, y_condensed, cbytes, cudaMemcpyHostToDevice, st.s));
+  tr.mark("h2d");
+  if (int e = b200w_dev_condensed_to_square(dY.as<double>(), n, dD.as<double>(), device, st.s)) return e;
+  if (int e = b200w_dev_linkage_average(dD.as<double>(), n, dZ.as<double>(), device, st.s)) return e;
+  tr.mark("nn-chain");
+  B200W_CUDA(cudaMemcpyAsync(Z_out, dZ.p, (size_t)(n - 1) * 4 * 8, cudaMemcpyDeviceToHost, st.s));
+  B200W_CUDA(cudaStreamSynchronize(st.s));
+  const int rc = b200w_linkage_finish(Z_out, n);
+  tr.mark("sort+label");
+  return rc;
+}
+
 extern "C" int b200w_intramodular(const double* A, int64_t n, const int32_t* labels, int nmod,
                                   const uint8_t* small, double* k_total, double* k_within,
                                   int device) {

@@ -6,27 +6,30 @@
 // exactly in integers: every standardised gene (a unit-norm row of Z, |z| <= 1) is scaled by 2^(46 - e_i), e_i
 // the binary exponent of its largest magnitude, rounded to a 46-bit integer and cut into S = 6 balanced base-256
 // digits (int8 planes).  cor_ij = 2^(e_i + e_j - 92) sum_{s,t} 256^(s+t) sum_k d^s_ik d^t_jk ; each inner sum is an
-// s8 x s8 GEMM accumulated exactly in int32.  The 21 digit pairs of weight w = s + t >= 5 are kept, plus the
-// pair (2, 2) of weight 4: for strongly correlated genes (and on the diagonal) the digits of equal planes are
-// themselves correlated, so that one dropped product is a coherent sum ~ K * 5e3 * 256^4 (measured: 2e-13 at
-// K = 200, 2e-11 for a gene with one dominant sample), while the dropped pairs of unequal planes stay random
-// (~1e-14).  The pairs of one weight share one TMEM accumulator, so a tile holds SEVEN 128 x 64 accumulators
-// (448 TMEM columns) and the epilogue combines them once:
-// (((((a10 * 256 + a9) * 256 + a8) ... ) * 256 + a5) * 256 + a4) * 2^32 * 2^(e_i + e_j - 92), every factor a power
+// s8 x s8 GEMM accumulated exactly in int32.  The 26 digit pairs of weight w = s + t >= 4 are kept.  (With w >= 5
+// the dropped pair (2, 2) showed up: for strongly correlated genes and on the diagonal the digits of EQUAL planes
+// are themselves correlated, so that product is a coherent sum ~ K * 5e3 * 256^4 -- measured 2e-13 at K = 200 and
+// 2e-11 for a gene with one dominant sample; the other pairs of weight 4 add ~3e-14 of noise at small K.  Below
+// weight 4 everything is under 1e-16.)  The pairs of one weight share one TMEM accumulator, so a tile holds SEVEN
+// 128 x 64 accumulators (448 TMEM columns) and the epilogue combines them once:
+// ((((((a10 * 256 + a9) * 256 + a8) ... ) * 256 + a5) * 256 + a4) * 2^32 * 2^(e_i + e_j - 92), every factor a power
 // of two, so cor_ij and cor_ji are bitwise equal and do not depend on the tile schedule or on the number of GPUs.
-// Measured against np.corrcoef: <= 2e-13 (tests/test_gpu_round2.py).
+// Measured against np.corrcoef: ~1e-15 (tests/test_gpu_round2.py).
 //
-// Kernel (persistent, one CTA per SM, 192 threads):
-//   warp 4     TMA producer: per 64-byte K step ONE box {64 B, 128 rows, 6 planes} of the row genes and one
+// Kernel (persistent, one CTA per SM, 320 threads):
+//   warp 8     TMA producer: per 64-byte K step ONE box {64 B, 128 rows, 6 planes} of the row genes and one
 //              {64 B, 64 rows, 6 planes} of the column genes (SWIZZLE_64B), 2-stage ring of 72 KB -- all 21
 //              pair products of a K step are issued from the same staged bytes (36 B/clk of L2 traffic per SM
 //              instead of 125 with a stage per pair)
-//   warp 5     TMEM allocation (512 columns) and MMA issue: 22 pairs x 2 tcgen05.mma M128 N64 K32 per stage
-//   warps 0-3  epilogue: drain the six accumulators (tcgen05.ld 32x32b.x16), combine, park the float64 tile in
-//              shared memory, release TMEM (the MMAs of the next tile run under the rest), then the epilogue of
-//              corr.cu's sweep_kernel on the parked tile: lane <-> column, power chain with the P column sums in
-//              registers, second pass with lane <-> row for tiles above the diagonal (symmetric schedule),
-//              optional similarity / adjacency output
+//   warp 9     TMEM allocation (512 columns) and MMA issue: 26 pairs x 2 tcgen05.mma M128 N64 K32 per stage
+//   warps 0-7  epilogue, two warps per scheduler so that FP64 latencies overlap (with four warps the kernel ran
+//              at 0.26 instructions per cycle and warp: profiles/r02_ncu_sweep_i8_v1.txt): every warp drains its
+//              own 32 x 32 part of the seven accumulators (tcgen05.ld 32x32b.x16), combines, parks it in shared
+//              memory and releases TMEM (the MMAs of the next tile run under the rest), then the epilogue of
+//              corr.cu's sweep_kernel on the parked part: lane <-> column, power chain with the column sums in
+//              registers (the number of powers is a template parameter: no branches inside the chain), second
+//              pass with lane <-> row for tiles above the diagonal (symmetric schedule), optional similarity /
+//              adjacency output
 #include <cuda.h>
 
 #include "sweep_common.cuh"
@@ -35,17 +38,18 @@ namespace b200w {
 
 constexpr int kZS = 6;                              // digit planes of Z
 constexpr int kZBits = 8 * kZS - 2;                 // 46
-constexpr int kZWmin = 5;                           // lowest digit-pair weight kept
-constexpr int kZAccHi = 2 * (kZS - 1) - kZWmin + 1;  // 6 accumulators, weights 5 .. 10
-constexpr int kZAcc = kZAccHi + 1;                  // + one for the pair (2, 2) of weight 4, see below
+constexpr int kZWmin = 4;                           // lowest digit-pair weight kept
+constexpr int kZAcc = 2 * (kZS - 1) - kZWmin + 1;   // 7 accumulators, weights 4 .. 10
 constexpr int kCKB = 64;                            // K bytes per stage
 constexpr int kCStages = 2;
-constexpr int kCThreads = 192;                      // warps 0-3 epilogue, 4 TMA, 5 MMA
+constexpr int kEpiWarps = 8, kTmaWarp = 8, kMmaWarp = 9;
+constexpr int kCThreads = 320;                      // warps 0-7 epilogue, 8 TMA, 9 MMA
 constexpr int kCAStage = kZS * kSweepBM * kCKB;     // 49152
 constexpr int kCBStage = kZS * kSweepBN * kCKB;     // 24576
 constexpr int kCStageBytes = kCAStage + kCBStage;   // 73728
-constexpr int kParkPitch = 65;                      // doubles; odd: row- and column-wise reads are conflict free
-constexpr int kParkDoubles = kSweepBM * kParkPitch;
+constexpr int kWarpPitch = 33;                      // doubles; odd: row- and column-wise reads are conflict free
+constexpr int kWarpPark = 32 * kWarpPitch;          // one epilogue warp's 32 x 32 sub-tile
+constexpr int kParkDoubles = kEpiWarps * kWarpPark; // (>= 2 * kSweepMaxP * 128 for the row-sum exchange)
 
 struct __align__(8) CorrBars {
   uint64_t full[kCStages], empty[kCStages], acc_full, acc_empty;
@@ -141,7 +145,7 @@ __device__ __forceinline__ uint64_t make_sw64_desc(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_i8_idesc(int M, int N) {
   return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 }  // namespace tc
 
 // ---- operand preparation: one CTA per (padded) gene row of Z -------------------------------------------------
@@ -225,6 +229,7 @@ struct TileWalk {
   }
 };
 
+template <int kP>
 __global__ void __launch_bounds__(kCThreads, 1)
 sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                 const __grid_constant__ SweepParams prm, const int nkb) {
@@ -237,16 +242,16 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
   __shared__ double col_scale[kBN];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 5 && lane == 0) {
+  if (warp == kMmaWarp && lane == 0) {
     for (int s = 0; s < kCStages; ++s) {
       tc::mbar_init(&bars->full[s], 1);
       tc::mbar_init(&bars->empty[s], 1);
     }
     tc::mbar_init(&bars->acc_full, 1);
-    tc::mbar_init(&bars->acc_empty, 4);  // lane 0 of every epilogue warp
+    tc::mbar_init(&bars->acc_empty, kEpiWarps);  // lane 0 of every epilogue warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) {
+  if (warp == kMmaWarp) {
     __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(&bars->tmem_base)),
                  "r"(512u) : "memory");
@@ -258,7 +263,7 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
   const uint32_t tmem_base = bars->tmem_base;
   const int64_t n = prm.n;
 
-  if (warp == 4) {
+  if (warp == kTmaWarp) {
     // ================================= TMA producer =================================
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmapA) : "memory");
@@ -279,7 +284,7 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       }
     }
     __syncwarp();
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     // ================================== MMA issuer ==================================
     if (lane == 0) {
       constexpr uint32_t idesc = tc::make_i8_idesc(kBM, kBN);
@@ -300,8 +305,8 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
           for (int s = kZS - 1; s >= 0; --s) {
 #pragma unroll
             for (int t = kZS - 1; t >= 0; --t) {
-              if (s + t < kZWmin && !(s == 2 && t == 2)) continue;
-              const int a = s + t >= kZWmin ? s + t - kZWmin : kZAccHi;  // (2, 2) has an accumulator of its own
+              if (s + t < kZWmin) continue;
+              const int a = s + t - kZWmin;
               const uint64_t adesc = tc::make_sw64_desc(a_addr + s * (kBM * kCKB));
               const uint64_t bdesc = tc::make_sw64_desc(b_addr + t * (kBN * kCKB));
               const uint32_t tmem_d = tmem_base + (uint32_t)(a * kBN);
@@ -316,13 +321,15 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
           }
           tc::commit(&bars->empty[stage]);  // frees the stage when these MMAs retire
         }
-        tc::commit(&bars->acc_full);  // all six accumulators complete -> epilogue
+        tc::commit(&bars->acc_full);  // all accumulators complete -> epilogue
       }
     }
     __syncwarp();
   } else {
-    // ============================= epilogue (warps 0-3) =============================
-    const int wm = warp >> 1, wn = warp & 1;
+    // ========================= epilogue (warps 0-7, two per scheduler) =========================
+    // warp = (wn, wm): rows 32 wm .. + 32 (its TMEM lane quarter), columns 32 wn .. + 32 -- a warp drains, parks
+    // and post-processes ITS OWN 32 x 32 sub-tile, so drain -> chain needs no CTA-wide barrier
+    const int wm = warp & 3, wn = warp >> 2;
     const int P = prm.P;
     const int64_t jend = prm.col0 + prm.ncols;
     double adj_power = prm.adj_power;
@@ -331,43 +338,46 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       adj_power = *prm.d_adj_power;
       adj_ipower = small_int_power(adj_power);
     }
-    const bool adj_mode = P == 0;
+    constexpr bool adj_mode = kP == 0;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     TileWalk w;
     w.init(prm);
     const int64_t jt_first = w.valid() ? w.jt : 0;
     int64_t cur_jt = -1;
     uint32_t tile_no = 0;
-    double kcol[kSweepMaxP];
+    double kcol[kP > 0 ? kP : 1];
 #pragma unroll
-    for (int p = 0; p < kSweepMaxP; ++p) kcol[p] = 0.0;
+    for (int p = 0; p < kP; ++p) kcol[p] = 0.0;
+    bool one[kP > 0 ? kP : 1];
+#pragma unroll
+    for (int p = 0; p < kP; ++p) one[p] = prm.istep[p] == 1;  // powers past prm.P have step 1 and are not stored
     const int col = wn * 32 + lane;
+    double* my = park + warp * kWarpPark;  // [row 0..31][col 0..31], pitch 33
 
     auto flush = [&](int64_t jt_done) {
-      // column sums of a finished column tile -> this CTA's slot; the two warps that share a column add up
-      // in a fixed order (deterministic, no atomics)
+      // column sums of a finished column tile -> this CTA's slot; the four warps that share a column add up
+      // in a fixed order (deterministic, no atomics); rare: once per column tile and CTA
       double* dst = prm.partial + ((int64_t)blockIdx.x * prm.max_seg + (jt_done - jt_first)) * P * kBN;
-      if (wm == 0) {
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        if (wm == q) {
 #pragma unroll
-        for (int p = 0; p < kSweepMaxP; ++p)
-          if (p < P) dst[p * kBN + col] = kcol[p];
-      }
-      tc::epi_barrier();
-      if (wm == 1) {
-#pragma unroll
-        for (int p = 0; p < kSweepMaxP; ++p)
-          if (p < P) dst[p * kBN + col] += kcol[p];
+          for (int p = 0; p < kP; ++p)
+            if (p < P) dst[p * kBN + col] = (q == 0 ? 0.0 : dst[p * kBN + col]) + kcol[p];
+        }
+        tc::epi_barrier();
       }
 #pragma unroll
-      for (int p = 0; p < kSweepMaxP; ++p) kcol[p] = 0.0;
+      for (int p = 0; p < kP; ++p) kcol[p] = 0.0;
     };
 
     for (; w.valid(); w.next(), ++tile_no) {
       const int64_t jt = w.jt, it = w.it, t = w.t;
       const int64_t j0 = prm.col0 + jt * kBN, i0 = it * kBM;
       const bool two_pass = w.sym && it < (jt >> 1);  // strictly above the diagonal block
-      tc::epi_barrier();  // every warp is done with the parked tile, bad_row, col_scale of the previous tile
+      tc::epi_barrier();  // every warp is done with bad_row, col_scale and the park of the previous tile
       if (jt != cur_jt) {
-        if (cur_jt >= 0 && P > 0) flush(cur_jt);
+        if (kP > 0 && cur_jt >= 0) flush(cur_jt);
         if (threadIdx.x < kBN) {
           const int64_t j = j0 + threadIdx.x;
           bad_col[threadIdx.x] = (j < jend) ? prm.bad[j] : 1;
@@ -376,70 +386,66 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
         }
         cur_jt = jt;
       }
-      {
-        const int64_t i = i0 + threadIdx.x;  // 128 threads = 128 rows
+      if (threadIdx.x < kBM) {
+        const int64_t i = i0 + threadIdx.x;
         bad_row[threadIdx.x] = (i < n) ? prm.bad[i] : 1;
       }
       tc::epi_barrier();
-      // ---- drain: thread <-> row (TMEM lane), the six accumulators combined in float64 ----
+      // ---- drain: lane <-> row (TMEM lane), this warp's 32 columns of the accumulators combined in float64 ----
       {
-        const int row = threadIdx.x;
-        const int64_t gi = i0 + row;
+        const int64_t gi = i0 + wm * 32 + lane;
         const double si = gi < n ? prm.zscale[gi] : 0.0;
         tc::mbar_wait(&bars->acc_full, tile_no & 1);
         tc::fence_after();
 #pragma unroll 1
-        for (int c = 0; c < kBN / 16; ++c) {
+        for (int c = 0; c < 2; ++c) {
           uint32_t r[kZAcc][16];
 #pragma unroll
           for (int a = 0; a < kZAcc; ++a)
-            tc::ld_32x32_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * kBN + c * 16), r[a]);
+            tc::ld_32x32_x16(tmem_base + ((uint32_t)(wm * 32) << 16) + (uint32_t)(a * kBN + wn * 32 + c * 16), r[a]);
           tc::ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            double v = (double)(int)r[kZAccHi - 1][j];
+            double v = (double)(int)r[kZAcc - 1][j];
 #pragma unroll
-            for (int a = kZAccHi - 2; a >= 0; --a) v = v * 256.0 + (double)(int)r[a][j];
-            v = v * 256.0 + (double)(int)r[kZAccHi][j];  // weight 4
-            park[row * kParkPitch + c * 16 + j] = v * (si * col_scale[c * 16 + j]);  // powers of two: exact
+            for (int a = kZAcc - 2; a >= 0; --a) v = v * 256.0 + (double)(int)r[a][j];
+            my[lane * kWarpPitch + c * 16 + j] = v * (si * col_scale[wn * 32 + c * 16 + j]);  // powers of two: exact
           }
         }
         tc::fence_before();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&bars->acc_empty);  // TMEM is free: the next tile's MMAs may start
+        if (lane == 0) tc::mbar_arrive(&bars->acc_empty);  // all 8 arrivals: the next tile's MMAs may start
       }
-      tc::epi_barrier();  // the whole tile is parked
-
+      // ---- first pass: lane <-> column, the warp's 32 rows eight at a time ----
       const int64_t gj = j0 + col;
       const bool cbad = bad_col[col];
-      const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-      double* my = park + (wm * 64) * kParkPitch + wn * 32;  // this warp's 64 x 32 sub-tile
+      const int rows_valid = (int)((n - i0 - wm * 32) < 32 ? (n - i0 - wm * 32) : 32);  // may be <= 0
+      const int diag_r = (int)((gj - (i0 + wm * 32)) >= 0 && (gj - (i0 + wm * 32)) < 32 ? gj - (i0 + wm * 32) : -1);
+      const bool col_in = gj < jend;
 
       // similarity and chain start of one element: wgcna.py:884-897, NaN skipped by nansum (:915); with prm.sim the
       // similarity (sweep) or s ** power (adjacency mode, wgcna.py:1111) is written the way WGCNA.adjacency forms
       // it: diagonal not forced, NaN rows and columns kept
       auto load = [&](int r, double& sv, double& c0) {
-        const int row = wm * 64 + r;
-        const int64_t gi = i0 + row;
-        double c = my[r * kParkPitch + lane];
+        double c = my[r * kWarpPitch + lane];
         c = fmin(1.0, fmax(-1.0, c));  // np.corrcoef clips to [-1, 1]
         sv = net_transform(c, prm.net_type);
         c0 = 1.0;
-        const bool nan_pair = cbad || bad_row[row];
+        const bool nan_pair = cbad || bad_row[wm * 32 + r];
         if (prm.sim != nullptr) {
           double s_out = sv;
           if (adj_mode) s_out = adj_ipower > 0 ? int_pow1(sv, adj_ipower) : pow(sv, adj_power);
           if (nan_pair) s_out = qnan;
-          if (prm.sim_transposed) my[r * kParkPitch + lane] = s_out;  // stored by the transposed pass below
-          else if (gi < n && gj < jend) prm.sim[gi * n + gj] = s_out;
+          if (prm.sim_transposed) my[r * kWarpPitch + lane] = s_out;  // stored by the transposed pass below
+          else if (r < rows_valid && col_in) prm.sim[(i0 + wm * 32 + r) * n + gj] = s_out;
         }
-        if (gi == gj) sv = 1.0;  // wgcna.py:897 (even for a NaN gene)
+        if (r == diag_r) sv = 1.0;  // wgcna.py:897 (even for a NaN gene)
         else if (nan_pair) { sv = 0.0; c0 = 0.0; }
-        if (gi >= n) { sv = 0.0; c0 = 0.0; }
+        if (r >= rows_valid) { sv = 0.0; c0 = 0.0; }
       };
 
 #pragma unroll 1
-      for (int r0 = 0; r0 < 64; r0 += 8) {
+      for (int r0 = 0; r0 < 32; r0 += 8) {
         double s1[8], s2[8], cur[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -447,94 +453,84 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
           s2[u] = s1[u] * s1[u];
         }
 #pragma unroll
-        for (int p = 0; p < kSweepMaxP; ++p) {
-          if (p < P) {  // wgcna.py:914  corxCur = corxPrev * corx ** step
-            const bool one = prm.istep[p] == 1;
+        for (int p = 0; p < kP; ++p) {  // wgcna.py:914  corxCur = corxPrev * corx ** step
 #pragma unroll
-            for (int u = 0; u < 8; ++u) cur[u] *= one ? s1[u] : s2[u];
-            kcol[p] += ((cur[0] + cur[1]) + (cur[2] + cur[3])) + ((cur[4] + cur[5]) + (cur[6] + cur[7]));
-          }
+          for (int u = 0; u < 8; ++u) cur[u] *= one[p] ? s1[u] : s2[u];
+          kcol[p] += ((cur[0] + cur[1]) + (cur[2] + cur[3])) + ((cur[4] + cur[5]) + (cur[6] + cur[7]));
         }
       }
       if (two_pass) {
-        // rows lane and lane + 32 of the warp's 64, its 32 columns four at a time: row sums for the genes of the
-        // tile's rows (their column tiles never visit these rows), and the mirrored half of the output
-        double kr[2][kSweepMaxP];
+        // lane <-> row: row sums over the warp's 32 columns, eight at a time, for the genes of the tile's rows
+        // (their column tiles never visit these rows), and the mirrored half of the output
+        double kr[kP > 0 ? kP : 1];
 #pragma unroll
-        for (int p = 0; p < kSweepMaxP; ++p) kr[0][p] = kr[1][p] = 0.0;
+        for (int p = 0; p < kP; ++p) kr[p] = 0.0;
+        const int64_t gi = i0 + wm * 32 + lane;
+        const bool rbad = bad_row[wm * 32 + lane];
+        const bool row_in = gi < n;
+        __syncwarp();
 #pragma unroll 1
-        for (int c0 = 0; c0 < 32; c0 += 4) {
+        for (int c0 = 0; c0 < 32; c0 += 8) {
           double s1[8], s2[8], cur[8];
 #pragma unroll
-          for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int r = h * 32 + lane, row = wm * 64 + r, colx = wn * 32 + c0 + u;
-              const int64_t gi = i0 + row, gjx = j0 + colx;
-              double c = my[r * kParkPitch + c0 + u];
-              c = fmin(1.0, fmax(-1.0, c));
-              double sv = net_transform(c, prm.net_type), c0v = 1.0;
-              const bool nan_pair = bad_col[colx] || bad_row[row];
-              const bool inside = gi < n && gjx < jend;
-              if (prm.sim != nullptr && inside) {
-                double s_out = sv;
-                if (adj_mode) s_out = adj_ipower > 0 ? int_pow1(sv, adj_ipower) : pow(sv, adj_power);
-                prm.sim[gjx * n + gi] = nan_pair ? qnan : s_out;
-              }
-              if (nan_pair || !inside) { sv = 0.0; c0v = 0.0; }
-              s1[h * 4 + u] = sv;
-              s2[h * 4 + u] = sv * sv;
-              cur[h * 4 + u] = c0v;
+          for (int u = 0; u < 8; ++u) {
+            const int colx = wn * 32 + c0 + u;
+            const int64_t gjx = j0 + colx;
+            double c = my[lane * kWarpPitch + c0 + u];
+            c = fmin(1.0, fmax(-1.0, c));
+            double sv = net_transform(c, prm.net_type), c0v = 1.0;
+            const bool nan_pair = bad_col[colx] || rbad;
+            const bool inside = row_in && gjx < jend;
+            if (prm.sim != nullptr && inside) {
+              double s_out = sv;
+              if (adj_mode) s_out = adj_ipower > 0 ? int_pow1(sv, adj_ipower) : pow(sv, adj_power);
+              prm.sim[gjx * n + gi] = nan_pair ? qnan : s_out;
             }
+            if (nan_pair || !inside) { sv = 0.0; c0v = 0.0; }
+            s1[u] = sv;
+            s2[u] = sv * sv;
+            cur[u] = c0v;
+          }
 #pragma unroll
-          for (int p = 0; p < kSweepMaxP; ++p) {
-            if (p < P) {
-              const bool one = prm.istep[p] == 1;
+          for (int p = 0; p < kP; ++p) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) cur[e] *= one ? s1[e] : s2[e];
-              kr[0][p] += (cur[0] + cur[1]) + (cur[2] + cur[3]);
-              kr[1][p] += (cur[4] + cur[5]) + (cur[6] + cur[7]);
-            }
+            for (int u = 0; u < 8; ++u) cur[u] *= one[p] ? s1[u] : s2[u];
+            kr[p] += ((cur[0] + cur[1]) + (cur[2] + cur[3])) + ((cur[4] + cur[5]) + (cur[6] + cur[7]));
           }
         }
-        if (P > 0) {
+        if (kP > 0) {
           // the two warps that share rows add up through the (now free) parking space: [wn][p][row]
           tc::epi_barrier();
 #pragma unroll
-          for (int p = 0; p < kSweepMaxP; ++p)
-            if (p < P) {
-              park[(wn * P + p) * kBM + wm * 64 + lane] = kr[0][p];
-              park[(wn * P + p) * kBM + wm * 64 + 32 + lane] = kr[1][p];
-            }
+          for (int p = 0; p < kP; ++p)
+            if (p < P) park[(wn * P + p) * kBM + wm * 32 + lane] = kr[p];
           tc::epi_barrier();
-          const int row = threadIdx.x;
-          double* dst = prm.rowpart + t * P * kBM;
-          for (int p = 0; p < P; ++p) dst[p * kBM + row] = park[p * kBM + row] + park[(P + p) * kBM + row];
+          if (threadIdx.x < kBM) {
+            const int row = threadIdx.x;
+            double* dst = prm.rowpart + t * P * kBM;
+            for (int p = 0; p < P; ++p) dst[p * kBM + row] = park[p * kBM + row] + park[(P + p) * kBM + row];
+          }
         }
       }
       if (prm.sim != nullptr && prm.sim_transposed) {  // lane <-> row of the sub-tile: 256-byte row segments
         __syncwarp();
+        const int64_t gi = i0 + wm * 32 + lane;
 #pragma unroll 1
         for (int c = 0; c < 32; ++c) {
           const int64_t gjc = j0 + wn * 32 + c;
           if (gjc >= jend) break;  // warp-uniform
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int r = h * 32 + lane;
-            const int64_t gi = i0 + wm * 64 + r;
-            if (gi < n) prm.sim[(gjc - prm.col0) * n + gi] = my[r * kParkPitch + c];
-          }
+          if (gi < n) prm.sim[(gjc - prm.col0) * n + gi] = my[lane * kWarpPitch + c];
         }
       }
     }
-    if (cur_jt >= 0 && P > 0) {
+    if (kP > 0 && cur_jt >= 0) {
       tc::epi_barrier();
       flush(cur_jt);
     }
   }
   tc::fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kMmaWarp) {
     tc::fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
@@ -567,7 +563,7 @@ bool corr_i8_enabled(int64_t m, int64_t n) {
   }
   // per accumulator |sum| <= K * 2^14 * (pairs of one weight <= 6) must stay below 2^31
   const int64_t ldkb = round_up(m, kCKB);
-  return prec != B200W_PREC_F64 && ldkb * 6 * 16384 < 2147483647LL && n >= 1;
+  return prec != B200W_PREC_F64 && ldkb * 6 * 16384 < 2147483647LL && n >= 1;  // (weight 5 has the most pairs: 6)
 }
 
 // One launch of the tcgen05 sweep / adjacency engine.  prm is filled by the caller as for corr.cu's sweep_kernel
@@ -600,9 +596,21 @@ int sweep_i8_launch(SweepParams prm, int64_t m, int64_t CT, int P, int G, int de
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(B200W_E_CUDA, "corr_i8: cuTensorMapEncodeTiled failed (%d)", (int)cr);
-  B200W_CUDA(cudaFuncSetAttribute(sweep_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCorrSmem));
-  sweep_i8_kernel<<<G, kCThreads, kCorrSmem, st>>>(tmapA, tmapB, prm, (int)(ldkb / kCKB));
-  B200W_LAUNCHED();
+  // the power count is a template parameter (no branches inside the chain); powers past prm.P multiply by s and
+  // are not stored
+  auto launch = [&](auto kern) -> int {
+    B200W_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCorrSmem));
+    kern<<<G, kCThreads, kCorrSmem, st>>>(tmapA, tmapB, prm, (int)(ldkb / kCKB));
+    B200W_LAUNCHED();
+    return 0;
+  };
+  int rc;
+  if (prm.P == 0) rc = launch(sweep_i8_kernel<0>);
+  else if (prm.P <= 2) rc = launch(sweep_i8_kernel<2>);
+  else if (prm.P <= 10) rc = launch(sweep_i8_kernel<10>);
+  else if (prm.P <= 15) rc = launch(sweep_i8_kernel<15>);
+  else rc = launch(sweep_i8_kernel<kSweepMaxP>);
+  if (rc) return rc;
   (void)CT;
   (void)P;
   (void)device;

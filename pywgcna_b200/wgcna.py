@@ -548,6 +548,25 @@ def network(datExpr, power=6, networkType="unsigned", TOMType="signed", TOMDenom
     return A, pd.DataFrame(T, copy=False)
 
 
+def linkage(y, method="average", metric="euclidean", optimal_ordering=False, device=None):
+    """``scipy.cluster.hierarchy.linkage(y, method="average")`` as ``findModules`` calls it on the condensed
+    ``round(1 - TOM, 8)`` (wgcna.py:326-328), computed on the GPU with scipy's exact merge order, heights and
+    labels (``b200w_linkage_average``).  ``y`` is the condensed distance vector; anything else scipy's
+    ``linkage`` accepts (other methods, observation matrices, optimal ordering) is handed to scipy."""
+    y = np.asarray(y)
+    if method != "average" or y.ndim != 1 or optimal_ordering or len(y) < 1:
+        from scipy.cluster.hierarchy import linkage as scipy_linkage
+
+        return scipy_linkage(y, method=method, metric=metric, optimal_ordering=optimal_ordering)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    n = int(round((1 + math.sqrt(1 + 8 * len(y))) / 2))
+    if n * (n - 1) // 2 != len(y):
+        raise ValueError("Incompatible vector size. It must be a binomial coefficient n choose 2 for some integer n >= 2.")
+    Z = np.empty((n - 1, 4), dtype=np.float64)
+    L.check(L.load().b200w_linkage_average(L.hptr(y), n, L.hptr(Z), _device(device)))
+    return Z
+
+
 def network_blocks(datExpr, *args, **kwargs):
     """Sharded host entry point: expression matrix in, this rank's row block of the TOM out (one process per
     GPU under torchrun); see ``pywgcna_b200.device.network_blocks``.  (Imported lazily: it needs torch.)"""
@@ -658,10 +677,12 @@ _PATCHED = ("pickSoftThreshold", "scaleFreeFitIndex", "calBlockSize", "checkSimi
 _saved = {}
 
 
-def install(target=None):
+def install(target=None, accelerate_linkage=True):
     """Rebind the hot-path static methods on the reference class so ``WGCNA.findModules()`` (which
     calls ``WGCNA.pickSoftThreshold / adjacency / TOMsimilarity`` by class name, wgcna.py:278, :310,
-    :320) runs them on the GPU.  ``target`` defaults to ``PyWGCNA.wgcna.WGCNA``."""
+    :320) runs them on the GPU.  ``target`` defaults to ``PyWGCNA.wgcna.WGCNA``.  With ``accelerate_linkage``
+    the module-level ``linkage`` that findModules calls next (wgcna.py:328) is rebound to the GPU average
+    linkage as well (same result as scipy's, bit for bit)."""
     if target is None:
         from PyWGCNA.wgcna import WGCNA as target  # noqa: N811
     L.load()  # fail now, not in the middle of findModules
@@ -673,6 +694,11 @@ def install(target=None):
     if (target, "CalculateSignedKME") not in _saved:
         _saved[(target, "CalculateSignedKME")] = target.__dict__.get("CalculateSignedKME")
     target.CalculateSignedKME = CalculateSignedKME  # an instance method in the reference
+    # findModules calls the module-level name `linkage` (from scipy.cluster.hierarchy, wgcna.py:10, :328)
+    mod = sys.modules.get(getattr(target, "__module__", ""), None)
+    if accelerate_linkage and mod is not None and hasattr(mod, "linkage") and (mod, "linkage") not in _saved:
+        _saved[(mod, "linkage")] = mod.linkage
+        mod.linkage = linkage
     return target
 
 
@@ -687,4 +713,7 @@ def uninstall(target=None):
             setattr(target, name, orig)
         elif name in target.__dict__:
             delattr(target, name)  # the class had no such attribute before install()
+    mod = sys.modules.get(getattr(target, "__module__", ""), None)
+    if mod is not None and (mod, "linkage") in _saved:
+        mod.linkage = _saved.pop((mod, "linkage"))
     return target

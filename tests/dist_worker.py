@@ -59,7 +59,7 @@ def main():
             if rank == 0:
                 one = DeviceNetwork(X, device=local, networkType="signed hybrid", world=1, rank=0, use_dist=False)
                 p1, _ = one.sft(powers)
-                A1 = one.adjacency(p1)
+                A1 = one.adjacency(p1).clone()  # (the sweep below reuses the adjacency buffer)
                 T1 = one.tom(TOMType="signed", TOMDenom="min")
                 k1 = one.sweep(powers).cpu().numpy()
                 torch.cuda.synchronize()

@@ -197,3 +197,41 @@ def test_ranks_real_nccl_and_ipc(gpu, world):
     assert rep["ok"] and len(rep["cases"]) == 8
     for c in rep["cases"]:
         assert c["tom_bitwise"] and c["adj_bitwise"] and c["power_equal"], c
+
+
+# ------------------------------------------------------------------------------------------------
+# average linkage on the GPU (findModules, wgcna.py:326-328) with scipy's exact result
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,dec", [(2, 8), (3, 8), (300, 2), (1000, 1), (1537, 8), (4000, 3)])
+def test_linkage_average_matches_scipy(gpu, n, dec):
+    """The whole linkage matrix -- merge order, heights, sizes -- bit for bit, also when rounding makes most
+    distances tie (dec = 1: ten distinct values), against scipy itself and the numpy restatement."""
+    from scipy.cluster.hierarchy import linkage as scipy_linkage
+    from scipy.spatial.distance import squareform
+
+    rng = np.random.default_rng(n * 10 + dec)
+    B = rng.random((n, n))
+    D = np.round((B + B.T) / 2, dec)
+    np.fill_diagonal(D, 0)
+    y = squareform(D, checks=False)
+    Z = bw.linkage(y, method="average")
+    Zs = scipy_linkage(y, method="average")
+    assert np.array_equal(Z, Zs)
+    if n <= 1000:
+        assert np.array_equal(Z, O.linkage_average(y))
+
+
+def test_linkage_on_gpu_dissimilarity_matches_reference_tree(gpu, golden_dir):
+    """End of the accelerated chain on the e2e fixture: GPU power -> adjacency -> round(1 - TOM, 8) condensed ->
+    GPU linkage gives the gene tree the unmodified reference built (merge order exact, heights to 2e-8)."""
+    g = load(golden_dir, "e2e_modules")
+    df = pd.DataFrame(g["X"])
+    p, _ = bw.pickSoftThreshold(df, networkType="signed hybrid", powerVector=list(g["powers"]))
+    A = bw.adjacency(df, adjacencyType="signed hybrid", power=p)
+    y = bw.dissTOM(A, TOMType="signed", condensed=True)
+    Z = bw.linkage(y, method="average")
+    from scipy.cluster.hierarchy import linkage as scipy_linkage
+
+    assert np.array_equal(Z, scipy_linkage(y, method="average"))
+    assert np.array_equal(Z[:, [0, 1, 3]], g["linkage"][:, [0, 1, 3]])
+    np.testing.assert_allclose(Z[:, 2], g["linkage"][:, 2], rtol=0, atol=2e-8)
