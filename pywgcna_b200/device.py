@@ -460,6 +460,22 @@ class DeviceNetwork:
         return T
 
 
+def _gene_tree(self, TOMType: str = "signed", TOMDenom: str = "min") -> np.ndarray:
+    """The gene tree of findModules (wgcna.py:320-328) without leaving the device: round(1 - TOM, 8) from the TOM
+    epilogue in square form, then the average-linkage kernel on it (the matrix is consumed), then scipy's sort
+    and labels on the n - 1 merges.  Single GPU (the walk is sequential); returns the scipy linkage matrix."""
+    if self.world != 1:
+        raise RuntimeError("gene_tree: gather the TOM row blocks on one GPU first")
+    D = self.tom(TOMType=TOMType, TOMDenom=TOMDenom, out_mode=L.OUT_DISS_R8)
+    Zraw = torch.empty((self.n - 1, 4), dtype=torch.float64, device=self.dev)
+    L.check(self.lib.b200w_dev_linkage_average(D.data_ptr(), self.n, Zraw.data_ptr(), self.device, self._stream()))
+    Z = np.ascontiguousarray(Zraw.cpu().numpy())
+    L.check(self.lib.b200w_linkage_finish(L.hptr(Z), self.n))
+    return Z
+
+
+DeviceNetwork.gene_tree = _gene_tree
+
 _NET_CACHE = {}
 
 

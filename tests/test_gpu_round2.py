@@ -235,3 +235,56 @@ def test_linkage_on_gpu_dissimilarity_matches_reference_tree(gpu, golden_dir):
     assert np.array_equal(Z, scipy_linkage(y, method="average"))
     assert np.array_equal(Z[:, [0, 1, 3]], g["linkage"][:, [0, 1, 3]])
     np.testing.assert_allclose(Z[:, 2], g["linkage"][:, 2], rtol=0, atol=2e-8)
+
+
+# ------------------------------------------------------------------------------------------------
+# C1 scale (192 x 23 844, the stand-in for the 5xFAD tutorial matrix): the reference's own results
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("net", ["signed hybrid", "unsigned"])
+def test_c1scale_power_tom_and_gene_tree(gpu, golden_dir, net):
+    """The accelerated part of findModules (wgcna.py:278-328) at the tutorial's size against what the UNMODIFIED
+    reference produced (tests/golden/c1scale_*.npz): selected power, soft-threshold table, sampled TOM rows, and
+    the gene tree -- merge order of all 23 843 merges identical, heights to 2e-8.  (cutreeHybrid on that tree takes
+    minutes of pure Python; the full chain through the real WGCNA.findModules runs in
+    test_c1scale_findmodules_labels / tools/e2e_c1scale.py.)"""
+    g = load(golden_dir, "c1scale_" + net.replace(" ", "_"))
+    m, n, F, seed, _, _ = CONFIGS["C1"]
+    tom = "signed" if net == "signed hybrid" else "unsigned"
+    X = make_expression(m, n, F=F, seed=seed)
+    df = pd.DataFrame(X)
+    p, sft = bw.pickSoftThreshold(df, networkType=net, powerVector=list(g["powers"]))
+    assert int(p) == int(g["power"])
+    got = sft.to_numpy(dtype=float)
+    np.testing.assert_allclose(got[:, 1:4], g["sft"][:, 1:4], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(got[:, 4:], g["sft"][:, 4:], rtol=1e-11, atol=1e-12)
+    A = bw.adjacency(df, adjacencyType=net, power=p)
+    T = bw.TOMsimilarity(A, TOMType=tom).to_numpy()
+    np.testing.assert_allclose(T[g["rows"]], g["tom_rows"], rtol=0, atol=1e-10)
+    del T
+    y = bw.dissTOM(A, TOMType=tom, condensed=True)  # round(1 - TOM, 8), squareform order (wgcna.py:323-326)
+    del A
+    Z = bw.linkage(y, method="average")              # wgcna.py:328 on the GPU
+    assert np.array_equal(Z[:, 0].astype(np.int32), g["link_a"])
+    assert np.array_equal(Z[:, 1].astype(np.int32), g["link_b"])
+    assert np.array_equal(Z[:, 3].astype(np.int32), g["link_n"])
+    np.testing.assert_allclose(Z[:, 2], g["link_h"], rtol=0, atol=2e-8)
+
+
+@pytest.mark.skipif(not os.environ.get("B200W_LONG_TESTS"), reason="~10 min of reference host code; set B200W_LONG_TESTS=1")
+def test_c1scale_findmodules_labels(gpu):
+    """pywgcna_b200.install() on the REAL PyWGCNA.wgcna.WGCNA (baseline/_ref), then its own findModules on the
+    C1-scale matrix for both network types and both TOM arithmetics: identical power, merge order, cutreeHybrid
+    labels and merged module labels (tools/e2e_c1scale.py; the outcome of the last run is committed as
+    profiles/r02_e2e_c1scale.json)."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = os.path.join(root, "gpurun_out", "e2e_c1scale_test.json")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "e2e_c1scale.py"), out], capture_output=True,
+                       text=True, timeout=3000, cwd=root)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    rep = json.load(open(out))
+    assert rep["ok"] and len(rep["results"]) == 4
