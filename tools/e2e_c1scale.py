@@ -42,6 +42,7 @@ def run_variant(variant):
     bw.wgcna.VERBOSE = False
     bw.install(W.WGCNA)  # the real class: findModules looks the three methods up on it by name (:278, :310, :320)
     assert W.WGCNA.__dict__["TOMsimilarity"].__func__ is bw.TOMsimilarity
+    assert W.linkage is bw.linkage  # wgcna.py:328 runs the GPU average linkage as well
     lib = bw._lib.load()
     launches0 = lib.b200w_launch_count()
     obj = H.make_wgcna(X, networkType=net, TOMType=tom)
@@ -76,13 +77,26 @@ def run_variant(variant):
 def main():
     out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out", "r02_e2e_c1scale.json")
     variants = sys.argv[2:] or VARIANTS
+    # every variant holds ~25 GB of host memory (adjacency, TOM, dissTOM as DataFrames): as many at a time as fit
+    try:
+        avail_gb = int(open("/proc/meminfo").read().split("MemAvailable:")[1].split()[0]) / 1e6
+    except Exception:
+        avail_gb = 64.0
+    try:  # a container's own limit, if it has one
+        lim = open("/sys/fs/cgroup/memory.max").read().strip()
+        if lim != "max":
+            avail_gb = min(avail_gb, int(lim) / 1e9 * 0.8)
+    except Exception:
+        pass
+    procs = max(1, min(len(variants), int(avail_gb // 40)))
     ctx = mp.get_context("spawn")
-    with ctx.Pool(len(variants)) as pool:
-        results = pool.map(run_variant, variants)
+    with ctx.Pool(procs, maxtasksperchild=1) as pool:
+        results = pool.map(run_variant, variants, chunksize=1)
     ok = all(r["power_identical"] and r["merge_order_identical"] and r["dynamic_labels_identical"]
              and r["module_labels_identical"] for r in results)
-    json.dump({"ok": ok, "results": results}, open(out, "w"), indent=1)
-    print(json.dumps({"ok": ok, "results": results}))
+    rep = {"ok": ok, "parallel_processes": procs, "host_mem_available_gb": round(avail_gb, 1), "results": results}
+    json.dump(rep, open(out, "w"), indent=1)
+    print(json.dumps(rep))
     sys.exit(0 if ok else 1)
 
 
