@@ -278,8 +278,9 @@ def run_reference(args):
         "e2e": {"value": cb["value"], "unit": "TFLOP/s", "seconds": cb["seconds"], "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
-    if wl == PRIMARY and not args.no_secondary:
-        # the like-for-like record: configs[1] at FULL size through the same unmodified functions
+    if wl == PRIMARY and not args.no_secondary and args.gpus == 1:
+        # the like-for-like record: configs[1] at FULL size through the same unmodified functions (once: the
+        # reference is a one-process CPU program, its numbers do not depend on --gpus)
         sb = cpu_time_workload(SECONDARY, 0, 1, args.ref_budget_s)
         line["secondary"] = {"config": config_of(SECONDARY, args.gpus), "value": sb["value"], "unit": "TFLOP/s",
                              "ms_per_step": sb["seconds"] * 1e3, "seconds": sb["seconds"], "steps": sb["steps"],

@@ -86,3 +86,58 @@ def test_row_block_partition_properties():
             for (a0, an), (b0, bn) in zip(blocks, blocks[1:]):
                 assert b0 == min(n, a0 + per) and an in (per, n - a0) or an == 0
             assert all(b[0] % 128 == 0 or b[1] == 0 for b in blocks)
+
+
+# ------------------------------------------------------------------------------------------------
+# the hardware parity probe of bench.py (every N > 1 line carries its result): the checker itself, on CPU
+# ------------------------------------------------------------------------------------------------
+class _FakeNet:
+    """The members of DeviceNetwork that bench.tom_parity_probe reads, over CPU tensors."""
+
+    def __init__(self, A_block, n, world, rank, per, row0):
+        self.A, self.n, self.world, self.rank, self.per = A_block, n, world, rank, per
+        self.row0, self.nrows = row0, A_block.shape[0]
+        self.dev = torch.device("cpu")
+
+
+def _probe_worker(rank, world, port, n, tom_type, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        import bench
+        from oracle import restated as O
+        from pywgcna_b200.synth import make_expression
+
+        X = make_expression(40, n, F=4, seed=n)
+        X[:, 3] = 1.0  # a NaN gene: the probe has to clean it like the TOM does (wgcna.py:1185)
+        A = O.adjacency(X, adjacencyType="unsigned", power=4)
+        T = O.TOMsimilarity(A.copy(), TOMType=tom_type).to_numpy()
+        per = shard.rows_per_rank(n, world, align=8)
+        r0, nr = shard.row_block(n, world, rank, align=8)
+        net = _FakeNet(torch.from_numpy(A[r0:r0 + nr].copy()), n, world, rank, per, r0)
+        good = bench.tom_parity_probe(net, torch.from_numpy(T[r0:r0 + nr].copy()), tom_type, rows_per_rank=8)
+        Tbad = T[r0:r0 + nr].copy()
+        last_with_rows = max(r for r in range(world) if shard.row_block(n, world, r, align=8)[1] > 0)
+        if rank == last_with_rows:
+            Tbad[:, 5] += 1e-6  # one rank's block is off: the max over ranks must show it
+        bad = bench.tom_parity_probe(net, torch.from_numpy(Tbad), tom_type, rows_per_rank=8)
+        if rank == 0:
+            np.save(os.path.join(out_dir, "probe.npy"), np.array([good["max_abs"], good["rows"], bad["max_abs"]]))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,tom_type", [(2, 97, "unsigned"), (3, 61, "signed"), (2, 6, "unsigned")])
+def test_bench_parity_probe_is_a_correct_checker(tmp_path, world, n, tom_type):
+    """bench.py's probe (sampled TOM rows against the float64 formula accumulated over the ranks' adjacency
+    blocks and all-reduced) agrees with the oracle to rounding when the blocks are right -- including a trailing
+    rank without rows (n = 6, world = 2, align 8) -- and reports a block that is off by 1e-6."""
+    mp.spawn(_probe_worker, args=(world, _free_port(), n, tom_type, str(tmp_path)), nprocs=world, join=True)
+    good, rows, bad = np.load(tmp_path / "probe.npy")
+    assert good < 1e-12 and rows >= 1
+    assert 5e-7 < bad < 2e-6

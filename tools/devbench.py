@@ -56,7 +56,7 @@ timeit("sweep", lambda: L.check(lib.b200w_dev_sweep(Z.data_ptr(), bad.data_ptr()
        flops=2 * m * n * n + 2 * P * n * n)
 timeit("adjacency", lambda: L.check(lib.b200w_dev_adjacency(Z.data_ptr(), bad.data_ptr(), m, n, 2, 6.0, 0, n, A.data_ptr(), dev, st)),
        flops=2 * m * n * n, bytes_=8 * n * n)
-stats = torch.empty(4, dtype=torch.float64, device="cuda")
+stats = torch.empty(6, dtype=torch.float64, device="cuda")
 timeit("check_adjacency", lambda: L.check(lib.b200w_dev_check_adjacency(A.data_ptr(), n, stats.data_ptr(), dev, st)), bytes_=8 * n * n)
 print("stats", stats.cpu().numpy())
 if not a.skip_tom:

@@ -90,12 +90,22 @@ def main():
         pass
     procs = max(1, min(len(variants), int(avail_gb // 40)))
     ctx = mp.get_context("spawn")
+    results = []
+
+    def report(final):
+        ok = all(r["power_identical"] and r["merge_order_identical"] and r["dynamic_labels_identical"]
+                 and r["module_labels_identical"] for r in results) and (not final or len(results) == len(variants))
+        rep = {"ok": ok, "complete": final, "parallel_processes": procs, "host_mem_available_gb": round(avail_gb, 1),
+               "results": sorted(results, key=lambda r: variants.index(r["variant"]))}
+        json.dump(rep, open(out, "w"), indent=1)
+        return rep
+
     with ctx.Pool(procs, maxtasksperchild=1) as pool:
-        results = pool.map(run_variant, variants, chunksize=1)
-    ok = all(r["power_identical"] and r["merge_order_identical"] and r["dynamic_labels_identical"]
-             and r["module_labels_identical"] for r in results)
-    rep = {"ok": ok, "parallel_processes": procs, "host_mem_available_gb": round(avail_gb, 1), "results": results}
-    json.dump(rep, open(out, "w"), indent=1)
+        for r in pool.imap_unordered(run_variant, variants, chunksize=1):
+            results.append(r)
+            report(False)  # partial results survive a timeout
+    rep = report(True)
+    ok = rep["ok"]
     print(json.dumps(rep))
     sys.exit(0 if ok else 1)
 
