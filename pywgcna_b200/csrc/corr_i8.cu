@@ -229,7 +229,8 @@ struct TileWalk {
   }
 };
 
-template <int kP>
+// kP: powers evaluated (>= prm.P); kAllOne: every step of the chain is 1 (consecutive powers): no selects
+template <int kP, bool kAllOne>
 __global__ void __launch_bounds__(kCThreads, 1)
 sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                 const __grid_constant__ SweepParams prm, const int nkb) {
@@ -455,7 +456,7 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
 #pragma unroll
         for (int p = 0; p < kP; ++p) {  // wgcna.py:914  corxCur = corxPrev * corx ** step
 #pragma unroll
-          for (int u = 0; u < 8; ++u) cur[u] *= one[p] ? s1[u] : s2[u];
+          for (int u = 0; u < 8; ++u) cur[u] *= (kAllOne || one[p]) ? s1[u] : s2[u];
           kcol[p] += ((cur[0] + cur[1]) + (cur[2] + cur[3])) + ((cur[4] + cur[5]) + (cur[6] + cur[7]));
         }
       }
@@ -494,7 +495,7 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
 #pragma unroll
           for (int p = 0; p < kP; ++p) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) cur[u] *= one[p] ? s1[u] : s2[u];
+            for (int u = 0; u < 8; ++u) cur[u] *= (kAllOne || one[p]) ? s1[u] : s2[u];
             kr[p] += ((cur[0] + cur[1]) + (cur[2] + cur[3])) + ((cur[4] + cur[5]) + (cur[6] + cur[7]));
           }
         }
@@ -604,12 +605,15 @@ int sweep_i8_launch(SweepParams prm, int64_t m, int64_t CT, int P, int G, int de
     B200W_LAUNCHED();
     return 0;
   };
+  bool all_one = true;
+  for (int p = 0; p < prm.P; ++p) all_one = all_one && prm.istep[p] == 1;
   int rc;
-  if (prm.P == 0) rc = launch(sweep_i8_kernel<0>);
-  else if (prm.P <= 2) rc = launch(sweep_i8_kernel<2>);
-  else if (prm.P <= 10) rc = launch(sweep_i8_kernel<10>);
-  else if (prm.P <= 15) rc = launch(sweep_i8_kernel<15>);
-  else rc = launch(sweep_i8_kernel<kSweepMaxP>);
+  if (prm.P == 0) rc = launch(sweep_i8_kernel<0, true>);
+  else if (prm.P <= 2) rc = launch(sweep_i8_kernel<2, false>);
+  else if (prm.P <= 10) rc = launch(sweep_i8_kernel<10, false>);
+  else if (prm.P <= 15) rc = launch(sweep_i8_kernel<15, false>);
+  else if (all_one) rc = launch(sweep_i8_kernel<kSweepMaxP, true>);
+  else rc = launch(sweep_i8_kernel<kSweepMaxP, false>);
   if (rc) return rc;
   (void)CT;
   (void)P;
