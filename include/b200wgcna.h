@@ -274,16 +274,17 @@ int b200w_dev_tom_compute_dist(const double* dA_rows, const void* d_operand, int
  * planes before the kernel starts, every rank keeps planes, scale and k in ONE shareable allocation
  * (b200w_dev_malloc of b200w_tom_shared_bytes(op_rows, n): planes at 0, scale at
  * b200w_tom_shared_scale_offset, k right behind it; d_operand / d_scale / d_k of the calls above point into
- * it) and, once all ranks have prepared their rows, calls b200w_dev_tom_pull_planes on a COPY stream: the
- * peers' rows of scale and k, then plane 4, 3, ... 0 are copied out of the peers' HBM by the copy engines
- * (peer_base[q] = rank q's allocation, peer-mapped), and after each plane d_plane_flags[s] is set to `epoch`
- * by a stream memory operation.  b200w_dev_tom_compute_dist_gated, launched at once on the compute stream,
- * starts with the pairs of the heaviest plane and waits at the first use of each further plane until its
- * flag has reached `epoch` (a wrapping 32-bit counter, incremented by the caller per exchange). */
+ * it) and, once all ranks have prepared their rows, calls b200w_dev_tom_pull_planes on a COPY stream: peer by
+ * peer (rank + 1, rank + 2, ...) the rows of scale, k and the five planes are copied out of that peer's HBM by
+ * the copy engines (peer_base[q] = rank q's allocation, peer-mapped), and after each peer d_plane_flags[q] is set
+ * to `epoch` by a stream memory operation.  b200w_dev_tom_compute_dist_gated, launched at once on the compute
+ * stream, visits its tiles in the same order -- first those whose column operand is local, then peer rank + 1,
+ * ... -- and its TMA producer waits at the first tile of each peer until that flag has reached `epoch` (a
+ * wrapping 32-bit counter the caller increments per exchange; d_plane_flags holds 8 words). */
 int64_t b200w_tom_shared_scale_offset(int64_t op_rows, int64_t n);
 int64_t b200w_tom_shared_bytes(int64_t op_rows, int64_t n);
 int b200w_dev_tom_pull_planes(void* d_local, void* const* peer_base, int world, int rank, int64_t per,
-                              int64_t op_rows, int64_t n, uint32_t* d_plane_flags /* B200W_I8_SLICES */,
+                              int64_t op_rows, int64_t n, uint32_t* d_plane_flags /* 8 words, one per rank */,
                               uint32_t epoch, int device, void* copy_stream);
 int b200w_dev_tom_compute_dist_gated(const double* dA_rows, const void* d_operand, int64_t op_rows,
                                      const double* d_scale, const double* d_k, int64_t n, int world, int rank,

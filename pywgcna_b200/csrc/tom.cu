@@ -383,8 +383,8 @@ extern "C" int b200w_dev_tom_compute_dist_gated(const double* dA_rows, const voi
                                tom_denom, out_mode, peer_out, d_plane_flags, plane_epoch, device, stream);
 }
 
-// Pull the other ranks' operand rows (digit planes, heaviest first, then nothing else: scale and k go first)
-// out of their HBM with the copy engines, and publish each plane's arrival to the contraction kernel.
+// Pull the other ranks' operand rows (scale, k and the digit planes), peer by peer, out of their HBM with the copy
+// engines, and publish each peer's arrival to the contraction kernel.
 typedef CUresult (*StreamWriteValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
 
 extern "C" int b200w_dev_tom_pull_planes(void* d_local, void* const* peer_base, int world, int rank, int64_t per,
@@ -419,11 +419,20 @@ extern "C" int b200w_dev_tom_pull_planes(void* d_local, void* const* peer_base, 
     }
     return cudaSuccess;
   };
-  B200W_CUDA(pull(scale_off, per * 8));
-  B200W_CUDA(pull(k_off, per * 8));
-  for (int s = B200W_I8_SLICES - 1; s >= 0; --s) {
-    B200W_CUDA(pull((int64_t)s * plane, per * ldn));
-    const CUresult r = write32((CUstream)cs, (CUdeviceptr)(d_plane_flags + s), epoch, 0);
+  for (int q = 1; q < world; ++q) {  // the order the contraction's tile list visits the peers in
+    const int src = (rank + q) % world;
+    if ((int64_t)src * per < n) {  // (a trailing rank without rows has nothing to give)
+      if (!peer_base[src]) return fail(B200W_E_INVALID, "tom_pull_planes: peer_base[%d] is NULL", src);
+      auto pull = [&](int64_t off, int64_t row_bytes) -> cudaError_t {
+        const int64_t at = off + (int64_t)src * per * row_bytes;
+        return cudaMemcpyAsync((char*)d_local + at, (const char*)peer_base[src] + at, (size_t)(per * row_bytes),
+                               cudaMemcpyDeviceToDevice, cs);
+      };
+      B200W_CUDA(pull(scale_off, 8));
+      B200W_CUDA(pull(k_off, 8));
+      for (int s = B200W_I8_SLICES - 1; s >= 0; --s) B200W_CUDA(pull((int64_t)s * plane, ldn));
+    }
+    const CUresult r = write32((CUstream)cs, (CUdeviceptr)(d_plane_flags + src), epoch, 0);
     if (r != CUDA_SUCCESS) return fail(B200W_E_CUDA, "tom_pull_planes: cuStreamWriteValue32 failed (%d)", (int)r);
   }
   return 0;

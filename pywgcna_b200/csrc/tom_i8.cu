@@ -65,10 +65,11 @@ struct I8Params {
   const double* scale_col;  // scale / k of the column operand (= scale / k unless A is asymmetric,
   const double* k_col;      //  TomColumnOperand)
   int32_t nan_mode;         // NaN rows / columns propagate (k = NaN marks them)
-  // sharded run with the exchange overlapped: plane s of the peers' operand rows is in place once
-  // plane_flags[s] has reached plane_epoch (written on the copy stream after the copies of that plane)
+  // sharded run with the exchange overlapped: the operand rows of rank q (all planes, scale, k) are in place
+  // once plane_flags[q] has reached plane_epoch (written on the copy stream after the copies from that peer)
   const unsigned int* plane_flags;
   unsigned int plane_epoch;
+  int32_t self_rank;
   double* out;           // nrows x n
   double* scratch;       // gridDim.x * 128 * 256
   int64_t n, row0, nrows;
@@ -395,6 +396,27 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
           tn = t2.y;
         }
         const int i0 = (int)(p.tile_row_base + tm * Cfg::kTileRows + rank * kTM), j0 = (int)(tn * kTN);
+        if (p.plane_flags != nullptr && active) {
+          // sharded run with the exchange overlapped: the column operand of this tile belongs to the rank that owns
+          // rows j0 ..; its rows (all digit planes, scale, k) are pulled by the copy engines while this kernel
+          // runs (b200w_dev_tom_pull_planes), peer by peer in the order the tile list visits them, and
+          // plane_flags[owner] reaches plane_epoch when they are in place.  Own rows need no wait.
+          const int64_t owner = (int64_t)j0 / p.per_rows;
+          if (owner != p.self_rank) {
+            unsigned int v, spins = 0;
+            uint64_t t0 = 0;
+            while (true) {
+              asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.plane_flags + owner) : "memory");
+              if ((int)(v - p.plane_epoch) >= 0) break;
+              if ((++spins & 1023u) == 0) {
+                const uint64_t now = global_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > kWaitLimitNs) __trap();
+              }
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");  // the TMA reads below must see the copied data
+          }
+        }
         for (int sg = 0; sg < p.nseg; ++sg) {
           const Seg sgm = p.seg[sg];
           // sync_mode 3: split barrier -- the arrival for segment g was posted kLead K-blocks before the
@@ -423,24 +445,6 @@ tom_i8_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ 
           if (!active) {
             if (split) atomicAdd(p.sync_ctr, 1u);  // arrival for the next segment
             continue;
-          }
-          if (p.plane_flags != nullptr) {
-            // the digit planes of the other ranks arrive heaviest first while this kernel runs (copy engines,
-            // b200w_dev_tom_pull_planes); segments are ordered heaviest weight first, so only the first use
-            // of a plane can actually wait
-            const int need = sgm.s < sgm.t ? sgm.s : sgm.t;  // planes arrive in descending order
-            unsigned int v, spins = 0;
-            uint64_t t0 = 0;
-            while (true) {
-              asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.plane_flags + need) : "memory");
-              if ((int)(v - p.plane_epoch) >= 0) break;
-              if ((++spins & 1023u) == 0) {
-                const uint64_t now = global_ns();
-                if (t0 == 0) t0 = now;
-                else if (now - t0 > kWaitLimitNs) __trap();
-              }
-            }
-            asm volatile("fence.proxy.async;" ::: "memory");  // the TMA reads below must see the copied data
           }
           const int arrive_kb = (sgm.kb1 - p.sync_lead > sgm.kb0) ? sgm.kb1 - p.sync_lead : sgm.kb0;
           for (int kb = sgm.kb0; kb < sgm.kb1; ++kb) {
@@ -806,6 +810,7 @@ int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t o
   prm.nan_mode = col ? col->nan_mode : 0;
   prm.plane_flags = d_plane_flags;
   prm.plane_epoch = plane_epoch;
+  prm.self_rank = rank;
   prm.out = d_out;
   prm.n = n;
   prm.row0 = row0;
@@ -869,9 +874,13 @@ int b200w_tom_compute_i8(const double* dA_rows, const void* d_operand, int64_t o
           tiles.push_back(oa == rank ? make_int2(a, b) : make_int2(b, a));
         }
       }
-      std::sort(tiles.begin(), tiles.end(), [G](const int2& x, const int2& y) {
-        const int kx[4] = {x.y / G, x.x / G, x.y, x.x}, ky[4] = {y.y / G, y.x / G, y.y, y.x};
-        for (int i = 0; i < 4; ++i)
+      // tiles whose column operand is local first, then the peers in the order their rows are pulled
+      // (rank + 1, rank + 2, ...: b200w_dev_tom_pull_planes), inside a group the super-block order
+      const int W = world;
+      std::sort(tiles.begin(), tiles.end(), [G, W, rank, &owner](const int2& x, const int2& y) {
+        const int dx = (owner(x.y) - rank + W) % W, dy = (owner(y.y) - rank + W) % W;
+        const int kx[5] = {dx, x.y / G, x.x / G, x.y, x.x}, ky[5] = {dy, y.y / G, y.x / G, y.y, y.x};
+        for (int i = 0; i < 5; ++i)
           if (kx[i] != ky[i]) return kx[i] < ky[i];
         return false;
       });

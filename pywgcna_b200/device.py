@@ -137,9 +137,9 @@ class DeviceNetwork:
         self.planes, self.elt = (1, 8) if elt == 8 else (elt, 1)
         self.fused = (self.world > 1 and self.elt == 1
                       and os.environ.get("B200WGCNA_DIST", "fused") != "rowblock")
-        # operand exchange of the fused mode: "pull" = copy engines fetch the peers' digit planes out of their
-        # HBM (heaviest plane first) while the contraction already runs, gated per plane; "gather" = NCCL
-        # all-gathers before the kernel starts
+        # operand exchange of the fused mode: "pull" = copy engines fetch the peers' operand rows out of their
+        # HBM, peer by peer, while the contraction already runs on the tiles whose operands are there (gated per
+        # peer); "gather" = NCCL all-gathers before the kernel starts
         self.pull = (self.fused and bool(self.use_dist)
                      and os.environ.get("B200WGCNA_EXCHANGE", "pull") == "pull")
         self._op_raw = None
