@@ -288,3 +288,46 @@ def test_c1scale_findmodules_labels(gpu):
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
     rep = json.load(open(out))
     assert rep["ok"] and len(rep["results"]) == 4
+
+
+# ------------------------------------------------------------------------------------------------
+# the one-call host entry and the device-resident gene tree
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("net,tom", [("signed hybrid", "signed"), ("unsigned", "unsigned")])
+def test_network_blocks_equals_three_calls(gpu, net, tom):
+    """pywgcna_b200.network_blocks (expression matrix in, TOM out, chain resident on the device, power selected on
+    the device) gives the reference-shaped three calls' results: same power, same table, bitwise the same adjacency
+    and TOM; a second call reuses the cached workspace."""
+    X = make_expression(64, 1700, F=6, seed=31)
+    X[:, 11] = 0.5  # a constant gene
+    df = pd.DataFrame(X)
+    powers = list(range(1, 11)) + list(range(11, 21, 2))
+    p, sft = bw.pickSoftThreshold(df, networkType=net, powerVector=powers)
+    A = bw.adjacency(df, adjacencyType=net, power=p)
+    T = bw.TOMsimilarity(A.copy(), TOMType=tom).to_numpy()
+    for _ in range(2):
+        res = bw.network_blocks(df, powerVector=powers, networkType=net, TOMType=tom, return_adjacency=True)
+        assert res["rows"] == (0, 1700) and int(res["power"]) == int(p)
+        np.testing.assert_allclose(res["sft"].to_numpy(dtype=float), sft.to_numpy(dtype=float), rtol=1e-12, atol=1e-13)
+        assert np.array_equal(res["adjacency"], A, equal_nan=True)
+        assert np.array_equal(res["TOM"], T)
+    from pywgcna_b200.device import release_workspace
+
+    release_workspace()
+
+
+def test_device_gene_tree_equals_scipy_on_host_dissimilarity(gpu):
+    """DeviceNetwork.gene_tree(): round(1 - TOM, 8) and the average linkage without leaving the device give the
+    linkage matrix scipy computes from the host-side dissTOM of the same network (wgcna.py:320-328)."""
+    from scipy.cluster.hierarchy import linkage as scipy_linkage
+    from scipy.spatial.distance import squareform
+
+    from pywgcna_b200.device import DeviceNetwork
+
+    X = make_expression(60, 1201, F=5, seed=41)
+    net = DeviceNetwork(X, device=0, networkType="signed hybrid")
+    net.adjacency(6.0)
+    Z = net.gene_tree(TOMType="signed")
+    A = bw.adjacency(pd.DataFrame(X), adjacencyType="signed hybrid", power=6)
+    diss = bw.dissTOM(A, TOMType="signed")
+    assert np.array_equal(Z, scipy_linkage(squareform(diss, checks=False), method="average"))
