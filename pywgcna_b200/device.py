@@ -45,8 +45,9 @@ class SftTable:
 
     COLUMNS = ("SFT.R.sq", "slope", "truncated R.sq", "mean(k)", "median(k)", "max(k)")
 
-    def __init__(self, event, host_bufs, powers, n, nBreaks, RsquaredCut, MeanCut):
+    def __init__(self, event, host_bufs, powers, n, nBreaks, RsquaredCut, MeanCut, owner=None, generation=0):
         self._event, self._bufs = event, host_bufs
+        self._owner, self._generation = owner, generation
         self.powers, self.n, self.nBreaks = powers, n, nBreaks
         self.RsquaredCut, self.MeanCut = RsquaredCut, MeanCut
         self._cols = None
@@ -55,6 +56,9 @@ class SftTable:
         if self._cols is None:
             from . import wgcna as W
 
+            if self._owner is not None and getattr(self._owner, "_sft_generation", 0) != self._generation:
+                raise RuntimeError("SftTable: a later sft() call of the same DeviceNetwork has reused the staging buffers; "
+                                   "read a table before asking for the next one")
             self._event.synchronize()
             h_stats, h_buck, h_fit, h_power, _ = self._bufs
             self._device_fit = h_fit.numpy().copy()
@@ -261,7 +265,9 @@ class DeviceNetwork:
         h_power.copy_(d_power, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.dev))
-        return d_power[0], SftTable(ev, self._sft_host, pv, self.n, nBreaks, RsquaredCut, MeanCut)
+        self._sft_generation = getattr(self, "_sft_generation", 0) + 1
+        return d_power[0], SftTable(ev, self._sft_host, pv, self.n, nBreaks, RsquaredCut, MeanCut, owner=self,
+                                    generation=self._sft_generation)
 
     def adjacency(self, power) -> torch.Tensor:
         """This rank's row block of the adjacency (wgcna.py:1097-1111), kept in HBM.  ``power`` is a number
