@@ -52,6 +52,14 @@ class AnnDataShim:
     def copy(self):
         return AnnDataShim(self.X.copy(), self.obs.copy(), self.var.copy())
 
+    def __getitem__(self, key):
+        """``adata[:, mask]`` as ``top_n_hub_genes`` slices it (wgcna.py:3746)."""
+        rows, cols = key
+        r = np.arange(self.X.shape[0])[rows] if not isinstance(rows, slice) or rows != slice(None) else slice(None)
+        c = np.asarray(cols)
+        return AnnDataShim(self.X[r][:, c], self.obs.iloc[r] if not isinstance(r, slice) else self.obs, self.var.loc[c]
+                           if c.dtype == bool else self.var.iloc[c])
+
 
 @contextlib.contextmanager
 def _reference_environment(W):

@@ -331,3 +331,48 @@ def test_device_gene_tree_equals_scipy_on_host_dissimilarity(gpu):
     A = bw.adjacency(pd.DataFrame(X), adjacencyType="signed hybrid", power=6)
     diss = bw.dissTOM(A, TOMType="signed")
     assert np.array_equal(Z, scipy_linkage(squareform(diss, checks=False), method="average"))
+
+
+# ------------------------------------------------------------------------------------------------
+# install() on the real reference class: the other callers of the rebound methods
+# ------------------------------------------------------------------------------------------------
+def test_install_on_real_class_hub_genes_and_signed_kme(gpu):
+    """The reference's own ``top_n_hub_genes`` (it calls ``WGCNA.adjacency`` by class name, wgcna.py:3748) and
+    ``CalculateSignedKME`` (:3452-3490), on a reference WGCNA object, before and after ``pywgcna_b200.install()`` on
+    the REAL class out of baseline/_ref: same genes in the same order, connectivity and kME to 1e-10; uninstall()
+    restores every attribute, also the module-level ``linkage``."""
+    from oracle import findmodules_harness as H
+    from oracle import ref_import as R
+
+    if not R.reference_available():
+        pytest.skip("no reference tree on this box (baseline/_ref missing)")
+    W = R.load_reference()
+    X, module = make_expression(80, 900, F=4, seed=77, return_modules=True)
+    obj = H.make_wgcna(X, networkType="signed hybrid")
+    obj.power = 6
+    obj.datExpr.var["moduleColors"] = np.array(["grey", "c0", "c1", "c2", "c3"], dtype=object)[module + 1]
+    rng = np.random.default_rng(3)
+    obj.datME = pd.DataFrame(rng.standard_normal((80, 3)), index=obj.datExpr.obs.index, columns=["MEa", "MEb", "MEc"])
+    before = {k: W.WGCNA.__dict__[k] for k in ("adjacency", "TOMsimilarity", "pickSoftThreshold", "CalculateSignedKME")}
+    scipy_linkage = W.linkage
+    with np.errstate(all="ignore"):
+        hub_ref = W.WGCNA.top_n_hub_genes(obj, "c1", n=25)
+        W.WGCNA.CalculateSignedKME(obj)
+    kme_ref = obj.signedKME.copy()
+    lib = _lib.load()
+    bw.install(W.WGCNA)
+    try:
+        assert W.linkage is bw.linkage
+        n0 = lib.b200w_launch_count()
+        hub = W.WGCNA.top_n_hub_genes(obj, "c1", n=25)
+        obj.CalculateSignedKME()
+        assert lib.b200w_launch_count() > n0  # the rebound methods ran on the GPU
+    finally:
+        bw.uninstall(W.WGCNA)
+    assert list(hub.index) == list(hub_ref.index)
+    np.testing.assert_allclose(hub["connectivity"].to_numpy(float), hub_ref["connectivity"].to_numpy(float), rtol=0, atol=1e-10)
+    assert list(obj.signedKME.columns) == list(kme_ref.columns)
+    np.testing.assert_allclose(obj.signedKME.to_numpy(float), kme_ref.to_numpy(float), rtol=0, atol=1e-10)
+    for k, v in before.items():
+        assert W.WGCNA.__dict__[k] is v
+    assert W.linkage is scipy_linkage

@@ -170,3 +170,39 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["full_workload"] is True and line["steps"] == 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["config"]["workload"].startswith("tiny") or "tiny" in json.dumps(line["config"])
+
+
+def test_install_rebinds_the_real_reference_class():
+    """install() / uninstall() on the REAL ``PyWGCNA.wgcna.WGCNA`` (imported through oracle/ref_import.py where a
+    reference tree exists): the names findModules looks up on the class (wgcna.py:278, :310, :320), the helpers, the
+    instance method CalculateSignedKME and the module-level ``linkage`` of :328 are rebound and restored."""
+    import pytest
+
+    from oracle import ref_import as R
+
+    if not R.reference_available():
+        pytest.skip("no reference tree here")
+    Wm = R.load_reference()
+    names = ("pickSoftThreshold", "adjacency", "TOMsimilarity", "TomSimilarityFromAdj", "checkAdjMat",
+             "softConnectivity", "intramodularConnectivity", "scaleFreeFitIndex", "calBlockSize", "checkSimilarity",
+             "CalculateSignedKME")
+    before = {k: Wm.WGCNA.__dict__[k] for k in names}
+    link = Wm.linkage
+    bw.install(Wm.WGCNA)
+    try:
+        for k in ("pickSoftThreshold", "adjacency", "TOMsimilarity"):
+            assert Wm.WGCNA.__dict__[k].__func__ is getattr(bw, k)
+            assert getattr(Wm.WGCNA, k) is getattr(bw, k)  # what `WGCNA.<name>(...)` resolves to
+        assert Wm.WGCNA.CalculateSignedKME is W.CalculateSignedKME
+        assert Wm.linkage is bw.linkage
+        bw.install(Wm.WGCNA)  # idempotent: the originals are remembered once
+    finally:
+        bw.uninstall(Wm.WGCNA)
+    for k, v in before.items():
+        assert Wm.WGCNA.__dict__[k] is v
+    assert Wm.linkage is link
+    bw.install(Wm.WGCNA, accelerate_linkage=False)
+    try:
+        assert Wm.linkage is link
+    finally:
+        bw.uninstall(Wm.WGCNA)
