@@ -256,6 +256,15 @@ int b200w_dev_tom_compute(const double* dA_rows /* nrows x n, original */, const
                           int64_t nrows, int tom_type, int tom_denom, int out_mode, int precision,
                           double* d_out /* nrows x n */, int device, void* stream);
 
+/* Step (3) on one GPU with the result delivered to HOST memory while the kernel is still running: finished
+ * row blocks are reported through host-mapped flags and copied out on a second stream (int8 precision, whole
+ * matrix, out_mode TOM / 1 - TOM / rounded).  d_out is the nrows x n device buffer the kernel writes; returns when
+ * out_host is complete. */
+int b200w_dev_tom_compute_to_host(const double* dA /* n x n, original */, const void* d_operand, int64_t op_rows,
+                                  const double* d_scale, const double* d_k, int64_t n, int tom_type,
+                                  int tom_denom, int out_mode, int precision, double* d_out, double* out_host,
+                                  int device, void* stream);
+
 /* Step (3) for several GPUs, symmetric and fused with its exchange.  TOM is symmetric, so only the
  * tiles on and above the diagonal are computed, dealt out over the `world` ranks; rank r owns the
  * output rows [r * per, (r + 1) * per) (per % 256 == 0) in ITS buffer peer_out[r] (per x n doubles).

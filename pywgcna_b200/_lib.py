@@ -76,6 +76,7 @@ SIGNATURES = {
     "b200w_dev_tom_prepare": (_int, [_dp, _i64, _i64, _i64, _int, _dp, _i64, _dp, _dp, _int, _dp]),
     "b200w_dev_tom_compute": (_int, [_dp, _dp, _i64, _dp, _dp, _i64, _i64, _i64, _int, _int, _int, _int,
                                      _dp, _int, _dp]),
+    "b200w_dev_tom_compute_to_host": (_int, [_dp, _dp, _i64, _dp, _dp, _i64, _int, _int, _int, _int, _dp, _dp, _int, _dp]),
     "b200w_dev_tom_compute_dist": (_int, [_dp, _dp, _i64, _dp, _dp, _i64, _int, _int, _i64, _int, _int, _int,
                                           C.POINTER(C.c_void_p), _int, _dp]),
     "b200w_tom_shared_scale_offset": (_i64, [_i64, _i64]),

@@ -497,6 +497,59 @@ extern "C" int b200w_check_adjacency(const double* A, int64_t n, double* stats, 
   return 0;
 }
 
+// Whole-matrix int8 contraction whose result goes to the host while the kernel is still running: the kernel
+// reports finished row blocks through host-mapped flags (symmetric schedule, row-major over super-blocks) and
+// this thread copies each block out on a second stream (at C3 20 GB of D2H take 0.39 s, the kernel 0.49 s).
+static int tom_compute_to_host(const double* dA, const void* dOp, int64_t op_rows, const double* dScale,
+                               const double* dK, int64_t n, int tom_type, int tom_denom, int out_mode, int w_min,
+                               const TomColumnOperand* colp, double* dOut, double* out_host, cudaStream_t s) {
+  TomProgress prog;
+  if (int e = b200w_tom_compute_i8(dA, dOp, op_rows, dScale, dK, n, 0, n, tom_type, tom_denom, out_mode, dOut, s, 1, 0,
+                                   0, nullptr, &prog, w_min, colp))
+    return e;
+  if (prog.nb > 0) {
+    Stream s2;
+    B200W_CUDA(s2.create());
+    for (int b = 0; b < prog.nb; ++b) {
+      unsigned long long spins = 0;
+      while (prog.flags[b] == 0u) {
+        if ((++spins & 0xfff) == 0 && cudaStreamQuery(s) != cudaErrorNotReady) break;  // kernel over (or failed)
+      }
+      const int64_t r0 = (int64_t)b * prog.rows_per_block;
+      const int64_t r1 = r0 + prog.rows_per_block < n ? r0 + prog.rows_per_block : n;
+      if (r1 > r0)
+        B200W_CUDA(cudaMemcpyAsync(out_host + r0 * n, dOut + r0 * n, (size_t)(r1 - r0) * n * 8,
+                                   cudaMemcpyDeviceToHost, s2.s));
+    }
+    B200W_CUDA(cudaStreamSynchronize(s));  // surfaces a kernel failure; all flags were set if it succeeded
+    B200W_CUDA(cudaStreamSynchronize(s2.s));
+    return 0;
+  }
+  B200W_CUDA(cudaMemcpyAsync(out_host, dOut, (size_t)n * n * 8, cudaMemcpyDeviceToHost, s));
+  B200W_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+extern "C" int b200w_dev_tom_compute_to_host(const double* dA, const void* d_operand, int64_t op_rows,
+                                             const double* d_scale, const double* d_k, int64_t n, int tom_type,
+                                             int tom_denom, int out_mode, int precision, double* d_out,
+                                             double* out_host, int device, void* stream) {
+  if (!dA || !d_operand || !d_scale || !d_k || !d_out || !out_host || n < 1)
+    return fail(B200W_E_INVALID, "tom_compute_to_host: bad args");
+  if (tom_type < 0 || tom_type > 1 || tom_denom < 0 || tom_denom > 1 || out_mode < 0 || out_mode > 2)
+    return fail(B200W_E_INVALID, "tom_compute_to_host: bad enum");
+  if (op_rows < round_up(n, 128) || op_rows % 128)
+    return fail(B200W_E_INVALID, "tom_compute_to_host: op_rows must be a multiple of 128 >= n");
+  precision = resolve_precision(precision);
+  if (!prec_is_i8(precision)) return fail(B200W_E_UNSUPPORTED, "tom_compute_to_host: int8 precision only");
+  if (int e = ensure_device(device)) return e;
+  HostPin pin;
+  pin.pin(out_host, (size_t)n * n * 8);
+  StreamDrain drain{(cudaStream_t)stream};
+  return tom_compute_to_host(dA, d_operand, op_rows, d_scale, d_k, n, tom_type, tom_denom, out_mode,
+                             prec_w_min(precision), nullptr, d_out, out_host, (cudaStream_t)stream);
+}
+
 // shared tail of b200w_tom / b200w_network: dA holds the full n x n adjacency on the device
 static int tom_from_device_adjacency(const double* dA, int64_t n, int tom_type, int tom_denom,
                                      int out_mode, int precision, int64_t row0, int64_t nrows,
@@ -549,32 +602,8 @@ static int tom_from_device_adjacency(const double* dA, int64_t n, int tom_type, 
     // (3.2 GB of D2H at C2 take 62 ms, the kernel 35 ms: the copy hides the kernel, not the reverse)
     if (tom_type < 0 || tom_type > 1 || tom_denom < 0 || tom_denom > 1 || out_mode < 0 || out_mode > 2)
       return fail(B200W_E_INVALID, "tom: bad enum");
-    TomProgress prog;
-    if (int e = b200w_tom_compute_i8(dA, dOp.p, op_rows, dScale.as<double>(), dK.as<double>(), n, 0, n, tom_type,
-                                     tom_denom, out_mode, dOut.as<double>(), s, 1, 0, 0, nullptr, &prog,
-                                     prec_w_min(precision), colp))
-      return e;
-    if (prog.nb > 0) {
-      Stream s2;
-      B200W_CUDA(s2.create());
-      for (int b = 0; b < prog.nb; ++b) {
-        unsigned long long spins = 0;
-        while (prog.flags[b] == 0u) {
-          if ((++spins & 0xfff) == 0 && cudaStreamQuery(s) != cudaErrorNotReady) break;  // kernel over (or failed)
-        }
-        const int64_t r0 = (int64_t)b * prog.rows_per_block;
-        const int64_t r1 = r0 + prog.rows_per_block < n ? r0 + prog.rows_per_block : n;
-        if (r1 > r0)
-          B200W_CUDA(cudaMemcpyAsync(out_host + r0 * n, dOut.as<double>() + r0 * n, (size_t)(r1 - r0) * n * 8,
-                                     cudaMemcpyDeviceToHost, s2.s));
-      }
-      B200W_CUDA(cudaStreamSynchronize(s));  // surfaces a kernel failure; all flags were set if it succeeded
-      B200W_CUDA(cudaStreamSynchronize(s2.s));
-      return 0;
-    }
-    B200W_CUDA(cudaMemcpyAsync(out_host, dOut.p, out_bytes, cudaMemcpyDeviceToHost, s));
-    B200W_CUDA(cudaStreamSynchronize(s));
-    return 0;
+    return tom_compute_to_host(dA, dOp.p, op_rows, dScale.as<double>(), dK.as<double>(), n, tom_type, tom_denom,
+                               out_mode, prec_w_min(precision), colp, dOut.as<double>(), out_host, s);
   }
   if (int e = tom_compute_impl(dA + row0 * n, dOp.p, op_rows, dScale.as<double>(), dK.as<double>(), n, row0,
                                nrows, tom_type, tom_denom, out_mode, precision, dOut.as<double>(), device, s, colp))

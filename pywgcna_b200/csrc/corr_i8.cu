@@ -17,10 +17,11 @@
 // Measured against np.corrcoef: ~1e-15 (tests/test_gpu_round2.py).
 //
 // Kernel (persistent, one CTA per SM, 320 threads):
-//   warp 8     TMA producer: per 64-byte K step ONE box {64 B, 128 rows, 6 planes} of the row genes and one
-//              {64 B, 64 rows, 6 planes} of the column genes (SWIZZLE_64B), 2-stage ring of 72 KB -- all 21
-//              pair products of a K step are issued from the same staged bytes (36 B/clk of L2 traffic per SM
-//              instead of 125 with a stage per pair)
+//   warp 8     TMA producer: per 64-byte K step ONE box {128 B, 128 rows, 3 plane pairs} of the row genes and one
+//              {128 B, 64 rows, 3 plane pairs} of the column genes (the planes are stored pairwise interleaved, so a
+//              box row is 128 bytes: with one 64-byte row per plane the kernel was bound by the TMA request rate),
+//              SWIZZLE_128B, 2-stage ring of 72 KB -- all 26 pair products of a K step are issued from the same
+//              staged bytes (36 B/clk of L2 traffic per SM instead of 125 with a stage per pair)
 //   warp 9     TMEM allocation (512 columns) and MMA issue: 26 pairs x 2 tcgen05.mma M128 N64 K32 per stage
 //   warps 0-7  epilogue, two warps per scheduler so that FP64 latencies overlap (with four warps the kernel ran
 //              at 0.26 instructions per cycle and warp: profiles/r02_ncu_sweep_i8_v1.txt): every warp drains its
@@ -128,16 +129,17 @@ __device__ __forceinline__ void ld_32x32_x16(uint32_t taddr, uint32_t (&r)[16]) 
       : "memory");
 }
 __device__ __forceinline__ void ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// K-major SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address [0,14) >> 4,
-// LBO [16,30) (unused for swizzled K-major, 1), SBO [32,46) = 8 rows * 64 B = 512 B, version [46,48) = 1,
-// layout type [61,64) = 4 (SWIZZLE_64B).  Tiles are 512-byte aligned.
-__device__ __forceinline__ uint64_t make_sw64_desc(uint32_t smem_addr) {
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address [0,14) >> 4,
+// LBO [16,30) (unused for swizzled K-major, 1), SBO [32,46) = 8 rows * 128 B = 1024 B, version [46,48) = 1,
+// layout type [61,64) = 2 (SWIZZLE_128B).  Tiles are 1024-byte aligned; a 32-byte K slice inside the 128-byte
+// atom is addressed by adding its byte offset (0, 32, 64, 96) to the start address.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
   d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)(1024 >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)4 << 61;
+  d |= (uint64_t)2 << 61;
   return d;
 }
 // instruction descriptor: c_format [4,6) = 2 (S32), a/b format [7,10) / [10,13) = 1 (signed int8), K-major both,
@@ -153,9 +155,12 @@ __global__ void __launch_bounds__(128)
 z_prepare_i8_kernel(const double* __restrict__ Z, int64_t n, int64_t ldk, int64_t ldkb, int64_t rows_pad,
                     int8_t* __restrict__ planes, double* __restrict__ zscale) {
   __shared__ double red[4];
+  // layout [plane pair q][row][K step of 64][128 B]: the 64 bytes of plane 2q, then those of plane 2q + 1 -- a TMA
+  // box row is 128 bytes (half as many, twice as long requests as one 64-byte row per plane) and the two planes of a
+  // pair sit in one SWIZZLE_128B atom, 64 bytes apart
   const int64_t i = blockIdx.x;
-  const int64_t plane_stride = rows_pad * ldkb;
-  int8_t* dst = planes + i * ldkb;
+  const int64_t pair_stride = rows_pad * ldkb * 2;
+  int8_t* dst = planes + i * ldkb * 2;
   double mx = 0.0;
   if (i < n)
     for (int64_t k = threadIdx.x; k < ldk; k += 128) mx = fmax(mx, fabs(Z[i * ldk + k]));
@@ -185,7 +190,8 @@ z_prepare_i8_kernel(const double* __restrict__ Z, int64_t n, int64_t ldk, int64_
       }
     }
 #pragma unroll
-    for (int p = 0; p < kZS; ++p) *reinterpret_cast<uint32_t*>(dst + p * plane_stride + k4) = packed[p];
+    for (int p = 0; p < kZS; ++p)
+      *reinterpret_cast<uint32_t*>(dst + (p >> 1) * pair_stride + (k4 >> 6) * 128 + (p & 1) * 64 + (k4 & 63)) = packed[p];
   }
 }
 
@@ -279,8 +285,8 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
           tc::mbar_wait(&bars->empty[stage], ((step >> 1) & 1) ^ 1);
           uint8_t* a_dst = smem + stage * kCStageBytes;
           tc::mbar_expect_tx(&bars->full[stage], kCStageBytes);
-          tc::tma_load_3d(a_dst, &tmapA, &bars->full[stage], kb * kCKB, i0, 0);
-          tc::tma_load_3d(a_dst + kCAStage, &tmapB, &bars->full[stage], kb * kCKB, j0, 0);
+          tc::tma_load_3d(a_dst, &tmapA, &bars->full[stage], kb * 128, i0, 0);
+          tc::tma_load_3d(a_dst + kCAStage, &tmapB, &bars->full[stage], kb * 128, j0, 0);
         }
       }
     }
@@ -308,12 +314,13 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
             for (int t = kZS - 1; t >= 0; --t) {
               if (s + t < kZWmin) continue;
               const int a = s + t - kZWmin;
-              const uint64_t adesc = tc::make_sw64_desc(a_addr + s * (kBM * kCKB));
-              const uint64_t bdesc = tc::make_sw64_desc(b_addr + t * (kBN * kCKB));
+              // plane p = pair p / 2 (a 128 rows x 128 B tile of its own), half p % 2 (64 bytes into the atom)
+              const uint64_t adesc = tc::make_sw128_desc(a_addr + (s >> 1) * (kBM * 128)) + (uint64_t)((s & 1) * 4);
+              const uint64_t bdesc = tc::make_sw128_desc(b_addr + (t >> 1) * (kBN * 128)) + (uint64_t)((t & 1) * 4);
               const uint32_t tmem_d = tmem_base + (uint32_t)(a * kBN);
 #pragma unroll
               for (int kk = 0; kk < kCKB / 32; ++kk) {
-                // K advance inside the 64-byte swizzle atom: +32 bytes on the start address (>> 4 = 2)
+                // K advance inside the swizzle atom: +32 bytes on the start address (>> 4 = 2)
                 tc::mma_i8(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
                            ((used >> a) & 1u) | (uint32_t)kk);
               }
@@ -584,17 +591,18 @@ int sweep_i8_launch(SweepParams prm, int64_t m, int64_t CT, int P, int G, int de
   prm.zscale = zscale.as<double>();
 
   CUtensorMap tmapA, tmapB;
-  const cuuint64_t gdim[3] = {(cuuint64_t)ldkb, (cuuint64_t)rows_pad, (cuuint64_t)kZS};
-  const cuuint64_t gstride[2] = {(cuuint64_t)ldkb, (cuuint64_t)ldkb * (cuuint64_t)rows_pad};
+  // [pair][row][2 ldkb bytes]: a box row = one K step of one gene = 64 B of plane 2q + 64 B of plane 2q + 1
+  const cuuint64_t gdim[3] = {(cuuint64_t)ldkb * 2, (cuuint64_t)rows_pad, (cuuint64_t)(kZS / 2)};
+  const cuuint64_t gstride[2] = {(cuuint64_t)ldkb * 2, (cuuint64_t)ldkb * 2 * (cuuint64_t)rows_pad};
   const cuuint32_t estr[3] = {1u, 1u, 1u};
-  const cuuint32_t boxA[3] = {(cuuint32_t)kCKB, (cuuint32_t)kSweepBM, (cuuint32_t)kZS};
-  const cuuint32_t boxB[3] = {(cuuint32_t)kCKB, (cuuint32_t)kSweepBN, (cuuint32_t)kZS};
+  const cuuint32_t boxA[3] = {128u, (cuuint32_t)kSweepBM, (cuuint32_t)(kZS / 2)};
+  const cuuint32_t boxB[3] = {128u, (cuuint32_t)kSweepBN, (cuuint32_t)(kZS / 2)};
   CUresult cr = encode(&tmapA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, planes.p, gdim, gstride, boxA, estr,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr == CUDA_SUCCESS)
     cr = encode(&tmapB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, planes.p, gdim, gstride, boxB, estr,
-                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return fail(B200W_E_CUDA, "corr_i8: cuTensorMapEncodeTiled failed (%d)", (int)cr);
   // the power count is a template parameter (no branches inside the chain); powers past prm.P multiply by s and

@@ -539,15 +539,26 @@ def network_blocks(datExpr, powerVector=None, networkType="unsigned", TOMType="s
         if net.nrows:
             L.check(lib.b200w_dev_download(L.hptr(a_host), A.data_ptr(), a_host.nbytes, dev, st))
         res["adjacency"] = a_host
-    T = net.tom(TOMType=TOMType, TOMDenom=TOMDenom, out_mode=out_mode)
+    t_host = L.result_empty((net.nrows, n))
+    overlapped = net.world == 1 and net.elt == 1 and out_mode in (L.OUT_TOM, L.OUT_DISS, L.OUT_DISS_R8)
+    if overlapped:
+        # one GPU: the result leaves the device row block by row block while the contraction is still running
+        net.tom_prepare()
+        tt, td = L.TOM_TYPES.index(TOMType), L.TOM_DENOMS.index(TOMDenom)
+        T = net._out()
+    else:
+        T = net.tom(TOMType=TOMType, TOMDenom=TOMDenom, out_mode=out_mode)
     if picked:
         # the host half of the soft-threshold table (2 x P ten-point regressions) runs while the GPU works
         names = ["Power", "SFT.R.sq", "slope", "truncated R.sq", "mean(k)", "median(k)", "max(k)"]
         sft = pd.DataFrame({"Power": pv, **{c: cols[c] for c in names[1:]}}, columns=names).astype(object)
         power = type(pv[0])(cols.device_power)
     res["power"], res["sft"] = power, sft
-    t_host = L.result_empty((net.nrows, n))
-    if net.nrows:
+    if overlapped:
+        L.check(lib.b200w_dev_tom_compute_to_host(net._A_rows.data_ptr(), net._op.data_ptr(), net.op_rows,
+                                                  net._scale.data_ptr(), net._k.data_ptr(), n, tt, td, out_mode,
+                                                  net.prec, T.data_ptr(), L.hptr(t_host), dev, st))
+    elif net.nrows:
         L.check(lib.b200w_dev_download(L.hptr(t_host), T.data_ptr(), t_host.nbytes, dev, st))
     res["TOM"] = t_host
     return res
