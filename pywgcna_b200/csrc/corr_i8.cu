@@ -425,31 +425,40 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
         if (lane == 0) tc::mbar_arrive(&bars->acc_empty);  // all 8 arrivals: the next tile's MMAs may start
       }
       // ---- first pass: lane <-> column, the warp's 32 rows eight at a time ----
+      // everything that does not depend on the element is hoisted: NaN flags of the 32 rows / columns as ballot
+      // masks, validity as masks, the output pointer advanced by n per row
       const int64_t gj = j0 + col;
+      const int64_t row_base = i0 + wm * 32;
       const bool cbad = bad_col[col];
-      const int rows_valid = (int)((n - i0 - wm * 32) < 32 ? (n - i0 - wm * 32) : 32);  // may be <= 0
-      const int diag_r = (int)((gj - (i0 + wm * 32)) >= 0 && (gj - (i0 + wm * 32)) < 32 ? gj - (i0 + wm * 32) : -1);
+      const int rows_valid = (int)((n - row_base) < 32 ? (n - row_base) : 32);  // may be <= 0
+      const int diag_r = (int)((gj - row_base) >= 0 && (gj - row_base) < 32 ? gj - row_base : -1);
       const bool col_in = gj < jend;
+      const unsigned rbad_mask = __ballot_sync(0xffffffffu, bad_row[wm * 32 + lane] != 0);
+      const unsigned cbad_mask = __ballot_sync(0xffffffffu, cbad);
+      const unsigned rvalid_mask = rows_valid >= 32 ? 0xffffffffu : (rows_valid <= 0 ? 0u : ((1u << rows_valid) - 1u));
+      const bool write_direct = prm.sim != nullptr && !prm.sim_transposed && col_in;
+      const bool keep_out = prm.sim != nullptr && prm.sim_transposed;
+      double* out_ptr = prm.sim != nullptr ? prm.sim + row_base * n + gj : nullptr;
+      const int net_type = prm.net_type;
 
-      // similarity and chain start of one element: wgcna.py:884-897, NaN skipped by nansum (:915); with prm.sim the
-      // similarity (sweep) or s ** power (adjacency mode, wgcna.py:1111) is written the way WGCNA.adjacency forms
-      // it: diagonal not forced, NaN rows and columns kept
-      auto load = [&](int r, double& sv, double& c0) {
-        double c = my[r * kWarpPitch + lane];
-        c = fmin(1.0, fmax(-1.0, c));  // np.corrcoef clips to [-1, 1]
-        sv = net_transform(c, prm.net_type);
-        c0 = 1.0;
-        const bool nan_pair = cbad || bad_row[wm * 32 + r];
-        if (prm.sim != nullptr) {
-          double s_out = sv;
-          if (adj_mode) s_out = adj_ipower > 0 ? int_pow1(sv, adj_ipower) : pow(sv, adj_power);
-          if (nan_pair) s_out = qnan;
-          if (prm.sim_transposed) my[r * kWarpPitch + lane] = s_out;  // stored by the transposed pass below
-          else if (r < rows_valid && col_in) prm.sim[(i0 + wm * 32 + r) * n + gj] = s_out;
+      // similarity of one element (wgcna.py:884-889 / :1102-1107) and what goes out with prm.sim: the similarity
+      // (sweep) or s ** power (adjacency mode, :1111) the way WGCNA.adjacency forms it -- diagonal not forced, NaN
+      // rows and columns kept.  Straight-line: the integer power is a fixed sequence of uniformly predicated
+      // multiplications (same order as int_pow4: bitwise the adjacency of the DMMA route).
+      auto out_value = [&](double sv) -> double {
+        if (!adj_mode) return sv;
+        if (adj_ipower <= 0) return pow(sv, adj_power);
+        double r = 1.0, b = sv;
+#pragma unroll
+        for (int bit = 0; bit < 7; ++bit) {
+          if ((adj_ipower >> bit) & 1) r *= b;
+          if ((adj_ipower >> (bit + 1)) != 0) b *= b;
         }
-        if (r == diag_r) sv = 1.0;  // wgcna.py:897 (even for a NaN gene)
-        else if (nan_pair) { sv = 0.0; c0 = 0.0; }
-        if (r >= rows_valid) { sv = 0.0; c0 = 0.0; }
+        return r;
+      };
+      auto similarity = [&](double c) -> double {
+        c = fmin(1.0, fmax(-1.0, c));  // np.corrcoef clips to [-1, 1]
+        return net_transform(c, net_type);
       };
 
 #pragma unroll 1
@@ -457,8 +466,24 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
         double s1[8], s2[8], cur[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          load(r0 + u, s1[u], cur[u]);
-          s2[u] = s1[u] * s1[u];
+          const int r = r0 + u;
+          double sv = similarity(my[r * kWarpPitch + lane]);
+          const bool nan_pair = cbad || ((rbad_mask >> r) & 1u);
+          const bool valid = (rvalid_mask >> r) & 1u;
+          if (prm.sim != nullptr) {
+            const double s_out = nan_pair ? qnan : out_value(sv);
+            if (keep_out) my[r * kWarpPitch + lane] = s_out;  // stored by the transposed pass below
+            else if (write_direct && valid) out_ptr[(int64_t)r * n] = s_out;
+          }
+          // chain start: the diagonal counts as 1 even for a NaN gene (wgcna.py:897), NaN pairs are skipped by
+          // nansum (:915), rows past the matrix contribute nothing
+          double c0 = 1.0;
+          if (r == diag_r) sv = 1.0;
+          else if (nan_pair) { sv = 0.0; c0 = 0.0; }
+          if (!valid) { sv = 0.0; c0 = 0.0; }
+          s1[u] = sv;
+          s2[u] = sv * sv;
+          cur[u] = c0;
         }
 #pragma unroll
         for (int p = 0; p < kP; ++p) {  // wgcna.py:914  corxCur = corxPrev * corx ** step
@@ -473,27 +498,25 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
         double kr[kP > 0 ? kP : 1];
 #pragma unroll
         for (int p = 0; p < kP; ++p) kr[p] = 0.0;
-        const int64_t gi = i0 + wm * 32 + lane;
-        const bool rbad = bad_row[wm * 32 + lane];
+        const int64_t gi = row_base + lane;
+        const bool rbad = (rbad_mask >> lane) & 1u;
         const bool row_in = gi < n;
+        const int64_t col_base = j0 + wn * 32;
+        const int cols_valid = (int)((jend - col_base) < 32 ? (jend - col_base) : 32);
+        const unsigned cvalid_mask = cols_valid >= 32 ? 0xffffffffu : (cols_valid <= 0 ? 0u : ((1u << cols_valid) - 1u));
+        double* mir_ptr = prm.sim != nullptr ? prm.sim + col_base * n + gi : nullptr;
         __syncwarp();
 #pragma unroll 1
         for (int c0 = 0; c0 < 32; c0 += 8) {
           double s1[8], s2[8], cur[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const int colx = wn * 32 + c0 + u;
-            const int64_t gjx = j0 + colx;
-            double c = my[lane * kWarpPitch + c0 + u];
-            c = fmin(1.0, fmax(-1.0, c));
-            double sv = net_transform(c, prm.net_type), c0v = 1.0;
-            const bool nan_pair = bad_col[colx] || rbad;
-            const bool inside = row_in && gjx < jend;
-            if (prm.sim != nullptr && inside) {
-              double s_out = sv;
-              if (adj_mode) s_out = adj_ipower > 0 ? int_pow1(sv, adj_ipower) : pow(sv, adj_power);
-              prm.sim[gjx * n + gi] = nan_pair ? qnan : s_out;
-            }
+            const int cx = c0 + u;
+            double sv = similarity(my[lane * kWarpPitch + cx]);
+            const bool nan_pair = rbad || ((cbad_mask >> cx) & 1u);
+            const bool inside = row_in && ((cvalid_mask >> cx) & 1u);
+            if (prm.sim != nullptr && inside) mir_ptr[(int64_t)cx * n] = nan_pair ? qnan : out_value(sv);
+            double c0v = 1.0;
             if (nan_pair || !inside) { sv = 0.0; c0v = 0.0; }
             s1[u] = sv;
             s2[u] = sv * sv;
