@@ -33,6 +33,8 @@
 //              adjacency output
 #include <cuda.h>
 
+#include <vector>
+
 #include "sweep_common.cuh"
 
 namespace b200w {
@@ -298,13 +300,17 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       TileWalk w;
       w.init(prm);
       uint32_t step = 0, tile_no = 0;
+      long long dbg_empty = 0, dbg_full = 0, dbg_t = clock64();
       for (; w.valid(); w.next(), ++tile_no) {
         tc::mbar_wait(&bars->acc_empty, (tile_no & 1) ^ 1);  // the epilogue has drained the previous tile
         tc::fence_after();
+        if (prm.debug) { const long long now = clock64(); dbg_empty += now - dbg_t; dbg_t = now; }
         for (int kb = 0; kb < nkb; ++kb, ++step) {
           const int stage = step & 1;
+          if (prm.debug) dbg_t = clock64();
           tc::mbar_wait(&bars->full[stage], (step >> 1) & 1);
           tc::fence_after();
+          if (prm.debug) { const long long now = clock64(); dbg_full += now - dbg_t; dbg_t = now; }
           const uint32_t a_addr = tc::smem_u32(smem + stage * kCStageBytes);
           const uint32_t b_addr = a_addr + kCAStage;
           uint32_t used = kb == 0 ? 0u : 0xffffffffu;  // accumulators that already hold a product of this tile
@@ -330,7 +336,9 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
           tc::commit(&bars->empty[stage]);  // frees the stage when these MMAs retire
         }
         tc::commit(&bars->acc_full);  // all accumulators complete -> epilogue
+        if (prm.debug) dbg_t = clock64();
       }
+      if (prm.debug) { prm.debug[blockIdx.x * 8 + 5] = dbg_empty; prm.debug[blockIdx.x * 8 + 6] = dbg_full; }
     }
     __syncwarp();
   } else {
@@ -379,10 +387,16 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       for (int p = 0; p < kP; ++p) kcol[p] = 0.0;
     };
 
+    long long dbg[5] = {0, 0, 0, 0, 0}, dbg_t = clock64(), dbg7 = 0, dbg_t7 = 0;
+    const bool dbg_on = prm.debug != nullptr && threadIdx.x == 0;
+    auto mark = [&](int slot) {
+      if (dbg_on) { const long long now = clock64(); dbg[slot] += now - dbg_t; dbg_t = now; }
+    };
     for (; w.valid(); w.next(), ++tile_no) {
       const int64_t jt = w.jt, it = w.it, t = w.t;
       const int64_t j0 = prm.col0 + jt * kBN, i0 = it * kBM;
       const bool two_pass = w.sym && it < (jt >> 1);  // strictly above the diagonal block
+      mark(4);
       tc::epi_barrier();  // every warp is done with bad_row, col_scale and the park of the previous tile
       if (jt != cur_jt) {
         if (kP > 0 && cur_jt >= 0) flush(cur_jt);
@@ -403,8 +417,10 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       {
         const int64_t gi = i0 + wm * 32 + lane;
         const double si = gi < n ? prm.zscale[gi] : 0.0;
+        mark(0);  // barriers + per-tile setup
         tc::mbar_wait(&bars->acc_full, tile_no & 1);
         tc::fence_after();
+        mark(1);  // waiting for the MMAs
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
           uint32_t r[kZAcc][16];
@@ -414,15 +430,23 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
           tc::ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            double v = (double)(int)r[kZAcc - 1][j];
+            // Horner in 64-bit integers (exact), two conversions instead of seven: I2F.F64 is a slow instruction and
+            // the drain sits on the critical path (the next tile's MMAs wait for it).  hi = weights 10 .. 7 (< 2^56),
+            // lo = weights 6 .. 4 (< 2^48); the sum is rounded once per part like any float64 evaluation would be.
+            long long hi = (long long)(int)r[kZAcc - 1][j];
 #pragma unroll
-            for (int a = kZAcc - 2; a >= 0; --a) v = v * 256.0 + (double)(int)r[a][j];
+            for (int a = kZAcc - 2; a >= 3; --a) hi = hi * 256 + (long long)(int)r[a][j];
+            long long lo = (long long)(int)r[2][j];
+            lo = lo * 256 + (long long)(int)r[1][j];
+            lo = lo * 256 + (long long)(int)r[0][j];
+            const double v = __ll2double_rn(hi) * 16777216.0 + __ll2double_rn(lo);
             my[lane * kWarpPitch + c * 16 + j] = v * (si * col_scale[wn * 32 + c * 16 + j]);  // powers of two: exact
           }
         }
         tc::fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&bars->acc_empty);  // all 8 arrivals: the next tile's MMAs may start
+        mark(2);  // drain
       }
       // ---- first pass: lane <-> column, the warp's 32 rows eight at a time ----
       // everything that does not depend on the element is hoisted: NaN flags of the 32 rows / columns as ballot
@@ -456,18 +480,39 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
         }
         return r;
       };
+      // clip to [-1, 1] (np.corrcoef) and the network transform WITHOUT float64 compares: on sm_100a DSETP /
+      // DMNMX-style instructions hold the FP64 pipe for tens of cycles (the first version of this loader spent
+      // 17 k of a tile's 33 k cycles in six of them per element) -- the sign and the "|c| >= 1" test are read off
+      // the high word with integer instructions; c is finite by construction (integer sums times powers of two)
+      double pre[16];
       auto similarity = [&](double c) -> double {
-        c = fmin(1.0, fmax(-1.0, c));  // np.corrcoef clips to [-1, 1]
-        return net_transform(c, net_type);
+        int hi = __double2hiint(c);
+        const int lo = __double2loint(c);
+        const bool neg = hi < 0;
+        const bool big = (hi & 0x7fffffff) >= 0x3ff00000;  // |c| >= 1  ->  +-1
+        const int ahi = big ? 0x3ff00000 : (hi & 0x7fffffff);
+        const int alo = big ? 0 : lo;
+        if (net_type == B200W_NET_UNSIGNED) return __hiloint2double(ahi, alo);                  // |c|
+        if (net_type == B200W_NET_SIGNED_HYBRID) return neg ? 0.0 : __hiloint2double(ahi, alo);  // max(c, 0)
+        return (1.0 + __hiloint2double(neg ? (ahi | 0x80000000) : ahi, alo)) / 2.0;              // (1 + c) / 2
       };
 
+      // Shared-memory loads issued one by one stall for hundreds of cycles while the tensor core streams its operands
+      // out of shared memory (N = 64 MMAs read 97 B/clk; measured: this pass took 17 k cycles inside the MMA window
+      // and 6 k outside), so 16 rows are fetched at once and their latencies overlap.
 #pragma unroll 1
-      for (int r0 = 0; r0 < 32; r0 += 8) {
+      for (int h0 = 0; h0 < 32; h0 += 16) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) pre[q] = my[(h0 + q) * kWarpPitch + lane];
+#pragma unroll
+      for (int g8 = 0; g8 < 16; g8 += 8) {
+        const int r0 = h0 + g8;
         double s1[8], s2[8], cur[8];
+        if (dbg_on) dbg_t7 = clock64();
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int r = r0 + u;
-          double sv = similarity(my[r * kWarpPitch + lane]);
+          double sv = similarity(pre[g8 + u]);
           const bool nan_pair = cbad || ((rbad_mask >> r) & 1u);
           const bool valid = (rvalid_mask >> r) & 1u;
           if (prm.sim != nullptr) {
@@ -485,6 +530,10 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
           s2[u] = sv * sv;
           cur[u] = c0;
         }
+        if (dbg_on) {  // loader share of the first pass (slot 7)
+          const long long now = clock64();
+          dbg7 += now - dbg_t7;
+        }
 #pragma unroll
         for (int p = 0; p < kP; ++p) {  // wgcna.py:914  corxCur = corxPrev * corx ** step
 #pragma unroll
@@ -492,6 +541,8 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
           kcol[p] += ((cur[0] + cur[1]) + (cur[2] + cur[3])) + ((cur[4] + cur[5]) + (cur[6] + cur[7]));
         }
       }
+      }
+      mark(3);  // first pass
       if (two_pass) {
         // lane <-> row: row sums over the warp's 32 columns, eight at a time, for the genes of the tile's rows
         // (their column tiles never visit these rows), and the mirrored half of the output
@@ -507,12 +558,17 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
         double* mir_ptr = prm.sim != nullptr ? prm.sim + col_base * n + gi : nullptr;
         __syncwarp();
 #pragma unroll 1
-        for (int c0 = 0; c0 < 32; c0 += 8) {
+        for (int h0 = 0; h0 < 32; h0 += 16) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) pre[q] = my[lane * kWarpPitch + h0 + q];
+#pragma unroll
+        for (int g8 = 0; g8 < 16; g8 += 8) {
+          const int c0 = h0 + g8;
           double s1[8], s2[8], cur[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const int cx = c0 + u;
-            double sv = similarity(my[lane * kWarpPitch + cx]);
+            double sv = similarity(pre[g8 + u]);
             const bool nan_pair = rbad || ((cbad_mask >> cx) & 1u);
             const bool inside = row_in && ((cvalid_mask >> cx) & 1u);
             if (prm.sim != nullptr && inside) mir_ptr[(int64_t)cx * n] = nan_pair ? qnan : out_value(sv);
@@ -528,6 +584,7 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
             for (int u = 0; u < 8; ++u) cur[u] *= (kAllOne || one[p]) ? s1[u] : s2[u];
             kr[p] += ((cur[0] + cur[1]) + (cur[2] + cur[3])) + ((cur[4] + cur[5]) + (cur[6] + cur[7]));
           }
+        }
         }
         if (kP > 0) {
           // the two warps that share rows add up through the (now free) parking space: [wn][p][row]
@@ -554,10 +611,14 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
         }
       }
     }
+    mark(4);  // second pass, row-sum exchange, transposed stores
     if (kP > 0 && cur_jt >= 0) {
       tc::epi_barrier();
       flush(cur_jt);
     }
+    if (dbg_on)
+      for (int i = 0; i < 5; ++i) prm.debug[blockIdx.x * 8 + i] = dbg[i];
+    if (dbg_on) prm.debug[blockIdx.x * 8 + 7] = dbg7;
   }
   tc::fence_before();
   __syncthreads();
@@ -612,6 +673,14 @@ int sweep_i8_launch(SweepParams prm, int64_t m, int64_t CT, int P, int G, int de
                                                            zscale.as<double>());
   B200W_LAUNCHED();
   prm.zscale = zscale.as<double>();
+  prm.debug = nullptr;
+  Scratch dbg;
+  static const bool debug_on = getenv("B200W_CORR_DEBUG") != nullptr;
+  if (debug_on) {
+    B200W_CUDA(dbg.alloc((size_t)G * 8 * sizeof(long long), st));
+    B200W_CUDA(cudaMemsetAsync(dbg.p, 0, (size_t)G * 8 * sizeof(long long), st));
+    prm.debug = dbg.as<long long>();
+  }
 
   CUtensorMap tmapA, tmapB;
   // [pair][row][2 ldkb bytes]: a box row = one K step of one gene = 64 B of plane 2q + 64 B of plane 2q + 1
@@ -646,6 +715,19 @@ int sweep_i8_launch(SweepParams prm, int64_t m, int64_t CT, int P, int G, int de
   else if (all_one) rc = launch(sweep_i8_kernel<kSweepMaxP, true>);
   else rc = launch(sweep_i8_kernel<kSweepMaxP, false>);
   if (rc) return rc;
+  if (debug_on) {  // development aid: where the cycles of epilogue warp 0 and of the MMA warp go
+    std::vector<long long> h((size_t)G * 8);
+    B200W_CUDA(cudaMemcpyAsync(h.data(), dbg.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    B200W_CUDA(cudaStreamSynchronize(st));
+    double a[8] = {0};
+    for (int b = 0; b < G; ++b)
+      for (int i = 0; i < 8; ++i) a[i] += (double)h[(size_t)b * 8 + i] / G;
+    const double tiles = (double)prm.T / G;
+    fprintf(stderr, "[b200w] sweep_i8 P=%d: per tile (cycles): setup+barriers %.0f  wait MMA %.0f  drain %.0f  pass1 %.0f  "
+                    "(loader %.0f)  pass2+rest %.0f | MMA warp: wait drained %.0f  wait TMA %.0f  (%.0f tiles per CTA)\n",
+            prm.P, a[0] / tiles, a[1] / tiles, a[2] / tiles, a[3] / tiles, a[7] / tiles, a[4] / tiles, a[5] / tiles,
+            a[6] / tiles, tiles);
+  }
   (void)CT;
   (void)P;
   (void)device;

@@ -31,6 +31,7 @@ struct SweepParams {
   int adj_ipower;
   const double* d_adj_power;  // optional: the power in device memory (device-side selection)
   const double* zscale;       // per gene 2^(e - 46): Z = digits * zscale
+  long long* debug;           // optional (B200W_CORR_DEBUG=1): [CTA][8] cycles per phase of epilogue warp 0 / the MMA warp
 };
 
 __host__ __device__ __forceinline__ void sweep_range(int64_t T, int64_t G, int64_t b, int64_t& t0, int64_t& t1) {
