@@ -176,7 +176,7 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_ranks_real_nccl_and_ipc(gpu, world):
     """`world` processes, one per GPU (tests/dist_worker.py): the union of the ranks' TOM blocks is bit-identical
     to the single-GPU result and within 1e-10 of the float64 oracle, for both exchange modes and for sizes that
