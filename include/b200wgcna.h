@@ -97,6 +97,14 @@ int b200w_soft_threshold_stats(const double* X, int64_t m, int64_t n, const doub
                                int net_type, int nbreaks, double* stats_out, int64_t* buckets_out,
                                int device);
 
+/* GENE-MAJOR input: the same two calls for an expression matrix laid out genes x samples (Xt is n x m, C order) --
+ * what an F-ordered m x n array is, e.g. DataFrame.to_numpy() when pandas keeps its block gene-major.  Accepting it
+ * saves the caller a transposition of the whole matrix; the results are bit-identical to the sample-major calls. */
+int b200w_soft_threshold_stats_gm(const double* Xt, int64_t m, int64_t n, const double* steps, int P, int net_type,
+                                  int nbreaks, double* stats_out, int64_t* buckets_out, int device);
+int b200w_adjacency_gm(const double* Xt, int64_t m, int64_t n, int net_type, double power, int64_t row0,
+                       int64_t nrows, double* A_out, int device);
+
 /* WGCNA.adjacency, wgcna.py:1097-1111 (corrcoef, transform, ** power).
  *   A_out    nrows x n row block of the n x n adjacency */
 int b200w_adjacency(const double* X, int64_t m, int64_t n, int net_type, double power,
@@ -191,6 +199,9 @@ int b200w_set_correlation_precision(int precision);
 int64_t b200w_padded_k(int64_t m);
 int b200w_dev_standardize(const double* dX, int64_t m, int64_t n, double* dZ, uint8_t* d_bad,
                           int device, void* stream);
+/* the same for gene-major input (dXt is n x m) */
+int b200w_dev_standardize_gm(const double* dXt, int64_t m, int64_t n, double* dZ, uint8_t* d_bad,
+                             int device, void* stream);
 int b200w_dev_sweep(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t n,
                     const double* h_steps, int P, int net_type, int64_t col0, int64_t ncols,
                     double* d_k /* P x ncols */, int device, void* stream);

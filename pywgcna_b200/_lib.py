@@ -44,6 +44,9 @@ SIGNATURES = {
     "b200w_connectivity_sweep": (_int, [_dp, _i64, _i64, _dp, _int, _int, _dp, _dp, _int]),
     "b200w_sft_exp_buckets": (_int, []),
     "b200w_soft_threshold_stats": (_int, [_dp, _i64, _i64, _dp, _int, _int, _int, _dp, _dp, _int]),
+    "b200w_soft_threshold_stats_gm": (_int, [_dp, _i64, _i64, _dp, _int, _int, _int, _dp, _dp, _int]),
+    "b200w_adjacency_gm": (_int, [_dp, _i64, _i64, _int, _dbl, _i64, _i64, _dp, _int]),
+    "b200w_dev_standardize_gm": (_int, [_dp, _i64, _i64, _dp, _dp, _int, _dp]),
     "b200w_dev_sft_stats": (_int, [_dp, _int, _i64, _i64, _int, _dp, _dp, _int, _dp]),
     "b200w_adjacency": (_int, [_dp, _i64, _i64, _int, _dbl, _i64, _i64, _dp, _int]),
     "b200w_check_adjacency": (_int, [_dp, _i64, _dp, _int]),
@@ -136,6 +139,21 @@ def as_f64_matrix(x) -> np.ndarray:
     if a.ndim != 2:
         raise ValueError("expected a 2-D matrix")
     return a
+
+
+def as_f64_expression(x):
+    """``(array, gene_major)`` for an expression matrix (samples x genes) WITHOUT copying when it is float64 and
+    contiguous in either order: a C-ordered m x n array goes as it is (gene_major False); an F-ordered one -- what
+    ``DataFrame.to_numpy()`` returns when pandas keeps its block gene-major -- goes as its transpose, the C-ordered
+    n x m array the ``*_gm`` entry points take (gene_major True).  Anything else is converted like as_f64_matrix."""
+    if hasattr(x, "to_numpy"):
+        x = x.to_numpy()
+    a = np.asarray(x)
+    if a.ndim != 2:
+        raise ValueError("expected a 2-D matrix")
+    if a.dtype == np.float64 and not a.flags["C_CONTIGUOUS"] and a.flags["F_CONTIGUOUS"]:
+        return a.T, True
+    return np.ascontiguousarray(a, dtype=np.float64), False
 
 
 def result_empty(shape, dtype=np.float64) -> np.ndarray:

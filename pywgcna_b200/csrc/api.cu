@@ -412,9 +412,29 @@ extern "C" int b200w_connectivity_sweep(const double* X, int64_t m, int64_t n, c
   return 0;
 }
 
+static int soft_threshold_stats_impl(const double* X, int64_t m, int64_t n, const double* steps, int P, int net_type,
+                                     int nbreaks, double* stats_out, int64_t* buckets_out, int device, int gene_major);
+
 extern "C" int b200w_soft_threshold_stats(const double* X, int64_t m, int64_t n, const double* steps,
                                           int P, int net_type, int nbreaks, double* stats_out,
                                           int64_t* buckets_out, int device) {
+  return soft_threshold_stats_impl(X, m, n, steps, P, net_type, nbreaks, stats_out, buckets_out, device, 0);
+}
+extern "C" int b200w_soft_threshold_stats_gm(const double* Xt, int64_t m, int64_t n, const double* steps,
+                                             int P, int net_type, int nbreaks, double* stats_out,
+                                             int64_t* buckets_out, int device) {
+  return soft_threshold_stats_impl(Xt, m, n, steps, P, net_type, nbreaks, stats_out, buckets_out, device, 1);
+}
+
+static int standardize_any(const double* dX, int64_t m, int64_t n, double* dZ, uint8_t* dBad, int device, void* s,
+                           int gene_major) {
+  return gene_major ? b200w_dev_standardize_gm(dX, m, n, dZ, dBad, device, s)
+                    : b200w_dev_standardize(dX, m, n, dZ, dBad, device, s);
+}
+
+static int soft_threshold_stats_impl(const double* X, int64_t m, int64_t n, const double* steps, int P, int net_type,
+                                     int nbreaks, double* stats_out, int64_t* buckets_out, int device,
+                                     int gene_major) {
   if (!X || !steps || !stats_out || !buckets_out || m < 1 || n < 1 || P < 1 || nbreaks < 1 || nbreaks > 16)
     return fail(B200W_E_INVALID, "soft_threshold_stats: bad args");
   if (int e = ensure_device(device)) return e;
@@ -432,8 +452,7 @@ extern "C" int b200w_soft_threshold_stats(const double* X, int64_t m, int64_t n,
   B200W_CUDA(dS.alloc(sbytes));
   B200W_CUDA(dB.alloc(bbytes));
   B200W_CUDA(cudaMemcpyAsync(dX.p, X, (size_t)m * n * 8, cudaMemcpyHostToDevice, st.s));
-  if (int e = b200w_dev_standardize(dX.as<double>(), m, n, dZ.as<double>(), dBad.as<uint8_t>(),
-                                    device, st.s))
+  if (int e = standardize_any(dX.as<double>(), m, n, dZ.as<double>(), dBad.as<uint8_t>(), device, st.s, gene_major))
     return e;
   if (int e = b200w_dev_sweep(dZ.as<double>(), dBad.as<uint8_t>(), m, n, steps, P, net_type, 0, n,
                               dK.as<double>(), device, st.s))
@@ -447,8 +466,20 @@ extern "C" int b200w_soft_threshold_stats(const double* X, int64_t m, int64_t n,
   return 0;
 }
 
+static int adjacency_host_impl(const double* X, int64_t m, int64_t n, int net_type, double power, int64_t row0,
+                               int64_t nrows, double* A_out, int device, int gene_major);
+
 extern "C" int b200w_adjacency(const double* X, int64_t m, int64_t n, int net_type, double power,
                                int64_t row0, int64_t nrows, double* A_out, int device) {
+  return adjacency_host_impl(X, m, n, net_type, power, row0, nrows, A_out, device, 0);
+}
+extern "C" int b200w_adjacency_gm(const double* Xt, int64_t m, int64_t n, int net_type, double power,
+                                  int64_t row0, int64_t nrows, double* A_out, int device) {
+  return adjacency_host_impl(Xt, m, n, net_type, power, row0, nrows, A_out, device, 1);
+}
+
+static int adjacency_host_impl(const double* X, int64_t m, int64_t n, int net_type, double power, int64_t row0,
+                               int64_t nrows, double* A_out, int device, int gene_major) {
   if (!X || !A_out || m < 1 || n < 1 || row0 < 0 || nrows < 1 || row0 + nrows > n)
     return fail(B200W_E_INVALID, "adjacency: bad args");
   if (int e = ensure_device(device)) return e;
@@ -468,8 +499,7 @@ extern "C" int b200w_adjacency(const double* X, int64_t m, int64_t n, int net_ty
   tr.mark("alloc");
   B200W_CUDA(cudaMemcpyAsync(dX.p, X, (size_t)m * n * 8, cudaMemcpyHostToDevice, st.s));
   tr.mark("h2d");
-  if (int e = b200w_dev_standardize(dX.as<double>(), m, n, dZ.as<double>(), dBad.as<uint8_t>(),
-                                    device, st.s))
+  if (int e = standardize_any(dX.as<double>(), m, n, dZ.as<double>(), dBad.as<uint8_t>(), device, st.s, gene_major))
     return e;
   if (int e = b200w_dev_adjacency(dZ.as<double>(), dBad.as<uint8_t>(), m, n, net_type, power, row0,
                                   nrows, dA.as<double>(), device, st.s))

@@ -59,6 +59,48 @@ standardize_kernel(const double* __restrict__ X, int64_t m, int64_t n, int64_t l
     __syncwarp();
   }
 }
+// K0 for GENE-MAJOR input (Xt is n x m: what DataFrame.to_numpy() hands out as an F-ordered m x n array when pandas
+// keeps its block gene-major -- accepted as it is instead of a 200 MB host-side transposition).  The arithmetic is
+// the same: left-to-right sum over the samples, so exactly-constant genes centre to exact zeros.  Phase 1: one thread
+// per gene (its samples are contiguous; sectors are reused from L1/L2); phase 2: coalesced normalisation.
+__global__ void __launch_bounds__(128)
+standardize_gm_stats_kernel(const double* __restrict__ Xt, int64_t m, int64_t n, double* __restrict__ mean_out,
+                            double* __restrict__ nrm_out, uint8_t* __restrict__ bad) {
+  const int64_t g = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (g >= n) return;
+  const double* row = Xt + g * m;
+  double sum = 0.0;
+  bool finite = true;
+  for (int64_t s = 0; s < m; ++s) {
+    const double x = row[s];
+    finite = finite && isfinite(x);
+    sum += x;
+  }
+  const double mean = sum / (double)m;
+  double ss = 0.0;
+  for (int64_t s = 0; s < m; ++s) {
+    const double d = row[s] - mean;
+    ss += d * d;
+  }
+  const bool is_bad = !finite || !(ss > 0.0);
+  bad[g] = is_bad ? 1 : 0;
+  mean_out[g] = mean;
+  nrm_out[g] = is_bad ? 0.0 : sqrt(ss);
+}
+
+__global__ void __launch_bounds__(256)
+standardize_gm_apply_kernel(const double* __restrict__ Xt, int64_t m, int64_t n, int64_t ldk,
+                            const double* __restrict__ mean, const double* __restrict__ nrm,
+                            double* __restrict__ Z) {
+  const int64_t g = blockIdx.x;
+  const double mu = mean[g], nr = nrm[g];
+  for (int64_t s = threadIdx.x; s < ldk; s += 256) {
+    double z = 0.0;
+    if (s < m && nr > 0.0) z = (Xt[g * m + s] - mu) / nr;
+    Z[g * ldk + s] = z;
+  }
+}
+
 // -------------------------------------------------------------------------------------------
 // Both kernels below use the narrow engine (gemm_f64.cuh: 128 x 64 tile, 4 warps, two CTAs per SM) and
 // hand the finished tile from the accumulator registers to the epilogue through the -- by then idle --
@@ -595,6 +637,23 @@ extern "C" int b200w_dev_standardize(const double* dX, int64_t m, int64_t n, dou
   int64_t warps = (n + 31) / 32;
   unsigned blocks = (unsigned)((warps + kStdWarps - 1) / kStdWarps);
   standardize_kernel<<<blocks, kStdWarps * 32, 0, st>>>(dX, m, n, ldk, dZ, d_bad);
+  B200W_LAUNCHED();
+  return 0;
+}
+
+extern "C" int b200w_dev_standardize_gm(const double* dXt, int64_t m, int64_t n, double* dZ, uint8_t* d_bad,
+                                        int device, void* stream) {
+  if (!dXt || !dZ || !d_bad || m < 1 || n < 1) return fail(B200W_E_INVALID, "standardize_gm: bad args");
+  if (int e = ensure_device(device)) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  Scratch mean, nrm;
+  B200W_CUDA(mean.alloc((size_t)n * 8, st));
+  B200W_CUDA(nrm.alloc((size_t)n * 8, st));
+  standardize_gm_stats_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(dXt, m, n, mean.as<double>(),
+                                                                          nrm.as<double>(), d_bad);
+  B200W_LAUNCHED();
+  standardize_gm_apply_kernel<<<(unsigned)n, 256, 0, st>>>(dXt, m, n, b200w_padded_k(m), mean.as<double>(),
+                                                           nrm.as<double>(), dZ);
   B200W_LAUNCHED();
   return 0;
 }

@@ -104,7 +104,7 @@ class DeviceNetwork:
 
     def __init__(self, X, device: int = 0, networkType: str = "unsigned", group=None, world: int | None = None,
                  rank: int | None = None, precision: str = "auto", use_dist: bool | None = None,
-                 keep_similarity: bool | None = None):
+                 keep_similarity: bool | None = None, gene_major: bool = False):
         self.lib = L.load()
         self.device = int(device)
         torch.cuda.set_device(self.device)
@@ -129,7 +129,9 @@ class DeviceNetwork:
             self.X = X.to(self.dev, torch.float64).contiguous()
         else:
             self.X = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).to(self.dev)
-        self.m, self.n = self.X.shape
+        # gene_major: X holds the expression matrix genes x samples (n x m), see b200w_dev_standardize_gm
+        self.gene_major = bool(gene_major)
+        self.m, self.n = self.X.shape[::-1] if self.gene_major else self.X.shape
         self.ldk = self.lib.b200w_padded_k(self.m)
         self.ldn = self.lib.b200w_padded_n(self.n)
         self.Z = torch.empty((self.n, self.ldk), dtype=torch.float64, device=self.dev)
@@ -179,8 +181,9 @@ class DeviceNetwork:
         return torch.cuda.current_stream(self.dev).cuda_stream
 
     def standardize(self):
-        L.check(self.lib.b200w_dev_standardize(self.X.data_ptr(), self.m, self.n, self.Z.data_ptr(),
-                                               self.bad.data_ptr(), self.device, self._stream()))
+        entry = self.lib.b200w_dev_standardize_gm if self.gene_major else self.lib.b200w_dev_standardize
+        L.check(entry(self.X.data_ptr(), self.m, self.n, self.Z.data_ptr(), self.bad.data_ptr(), self.device,
+                      self._stream()))
         self._standardized = True
         self._sim_in_A = False
 
@@ -508,20 +511,20 @@ def network_blocks(datExpr, powerVector=None, networkType="unsigned", TOMType="s
     ``adjacency`` (nrows x n)."""
     import pandas as pd
 
-    X = L.as_f64_matrix(datExpr)
+    X, gene_major = L.as_f64_expression(datExpr)  # no host-side transposition for an F-ordered matrix
     lib = L.load()
     dev = L.default_device() if device is None else int(device)
     torch.cuda.set_device(dev)
-    m, n = X.shape
+    m, n = X.shape[::-1] if gene_major else X.shape
     # the device workspace (and, under torchrun, the peer mappings: IPC handle exchange + cudaIpcOpenMemHandle
     # cost hundreds of ms) is kept between calls of the same shape, like the DevCache of the C entry points
     dist_on = torch.distributed.is_available() and torch.distributed.is_initialized()
-    key = (dev, m, n, networkType, precision, torch.distributed.get_world_size() if dist_on else 1)
+    key = (dev, m, n, networkType, precision, torch.distributed.get_world_size() if dist_on else 1, gene_major)
     net = _NET_CACHE.get(key)
     if net is None:
         _NET_CACHE.clear()  # one workspace at a time: these are tens of GB
-        net = DeviceNetwork(torch.empty((m, n), dtype=torch.float64, device=torch.device("cuda", dev)), device=dev,
-                            networkType=networkType, precision=precision)
+        net = DeviceNetwork(torch.empty(X.shape, dtype=torch.float64, device=torch.device("cuda", dev)), device=dev,
+                            networkType=networkType, precision=precision, gene_major=gene_major)
         _NET_CACHE[key] = net
     st = torch.cuda.current_stream(net.dev).cuda_stream
     L.check(lib.b200w_dev_upload(net.X.data_ptr(), L.hptr(X), X.nbytes, dev, st))

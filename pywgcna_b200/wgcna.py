@@ -347,16 +347,16 @@ def pickSoftThreshold(data, dataIsExpr=True, weights=None, RsquaredCut=0.9, Mean
     if 1 <= nBreaks <= 16:
         # sweep, histograms, medians and exact mantissa sums on the device (k never leaves HBM); only
         # the two 10-point regressions per power run on the host                       (:873-932)
-        X = L.as_f64_matrix(data)
-        m_, n_ = X.shape
+        X, gene_major = L.as_f64_expression(data)
+        m_, n_ = X.shape[::-1] if gene_major else X.shape
         pv = np.asarray(powerVector, dtype=np.float64)
         steps = np.ascontiguousarray(np.diff(np.concatenate(([0.0], pv))))  # :901-903
         lib = L.load()
         dstats = np.empty((len(pv), 4 + 2 * nBreaks), dtype=np.float64)
         dbuck = np.empty((len(pv), lib.b200w_sft_exp_buckets(), 2), dtype=np.int64)
-        L.check(lib.b200w_soft_threshold_stats(L.hptr(X), m_, n_, L.hptr(steps), len(pv),
-                                               networkTypes.index(networkType), nBreaks, L.hptr(dstats),
-                                               L.hptr(dbuck), _device(device)))
+        entry = lib.b200w_soft_threshold_stats_gm if gene_major else lib.b200w_soft_threshold_stats
+        L.check(entry(L.hptr(X), m_, n_, L.hptr(steps), len(pv), networkTypes.index(networkType), nBreaks,
+                      L.hptr(dstats), L.hptr(dbuck), _device(device)))
         stats = fit_table_from_stats(dstats, dbuck, n_, nBreaks)
     else:
         datk = connectivity(data, powerVector, networkType, device=device)
@@ -395,12 +395,13 @@ def adjacency(datExpr, selectCols=None, adjacencyType="unsigned", power=6, corOp
         raise NotImplementedError("weights: not supported (np.corrcoef ignores them in the reference too)")
     if selectCols is not None:
         raise NotImplementedError("selectCols: that branch of the reference is invalid for DataFrames (wgcna.py:1100)")
-    X = L.as_f64_matrix(datExpr)
-    m, n = X.shape
+    X, gene_major = L.as_f64_expression(datExpr)
+    m, n = X.shape[::-1] if gene_major else X.shape
     row0, nrows = (0, n) if rows is None else (int(rows[0]), int(rows[1]))
     out = L.result_empty((nrows, n))
-    L.check(L.load().b200w_adjacency(L.hptr(X), m, n, intType, float(power), row0, nrows, L.hptr(out),
-                                     _device(device)))
+    lib = L.load()
+    entry = lib.b200w_adjacency_gm if gene_major else lib.b200w_adjacency
+    L.check(entry(L.hptr(X), m, n, intType, float(power), row0, nrows, L.hptr(out), _device(device)))
     _say("\tDone..\n")
     return out
 

@@ -376,3 +376,29 @@ def test_install_on_real_class_hub_genes_and_signed_kme(gpu):
     for k, v in before.items():
         assert W.WGCNA.__dict__[k] is v
     assert W.linkage is scipy_linkage
+
+
+def test_gene_major_input_is_accepted_without_copy_and_gives_the_same_bits(gpu):
+    """An F-ordered expression matrix (what DataFrame.to_numpy() returns under pandas >= 3) is passed to the *_gm
+    entry points as it is; results equal the C-ordered calls bit for bit, including a constant and a NaN gene."""
+    X = make_expression(57, 1111, F=5, seed=51)
+    X[:, 5] = 2.0
+    X[3, 9] = np.nan
+    Xc, Xf = np.ascontiguousarray(X), np.asfortranarray(X)
+    a, gm = _lib.as_f64_expression(Xf)
+    assert gm and np.shares_memory(a, Xf) and not _lib.as_f64_expression(Xc)[1]
+    assert _lib.as_f64_expression(pd.DataFrame(Xc))[0].shape in ((57, 1111), (1111, 57))
+    powers = list(range(1, 21))
+    p0, t0 = bw.pickSoftThreshold(Xc, networkType="signed", powerVector=powers)
+    p1, t1 = bw.pickSoftThreshold(Xf, networkType="signed", powerVector=powers)
+    assert p0 == p1 and np.array_equal(t0.to_numpy(dtype=float), t1.to_numpy(dtype=float), equal_nan=True)
+    A0 = bw.adjacency(Xc, adjacencyType="signed", power=7)
+    A1 = bw.adjacency(Xf, adjacencyType="signed", power=7)
+    assert np.array_equal(A0, A1, equal_nan=True)
+    r0 = bw.network_blocks(Xc, powerVector=powers, networkType="signed", TOMType="signed")
+    T0 = r0["TOM"].copy()
+    r1 = bw.network_blocks(Xf, powerVector=powers, networkType="signed", TOMType="signed")
+    assert r0["power"] == r1["power"] and np.array_equal(T0, r1["TOM"])
+    from pywgcna_b200.device import release_workspace
+
+    release_workspace()
