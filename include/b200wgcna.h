@@ -217,6 +217,18 @@ int b200w_dev_sweep_similarity(const double* dZ, const uint8_t* d_bad, int64_t m
                                void* stream);
 int b200w_dev_adjacency_from_similarity(double* d_sim_inout /* nrows x n */, int64_t nrows, int64_t n,
                                         double power, int device, void* stream);
+/* The sweep for several GPUs with the SYMMETRIC schedule (tcgen05 engine, power steps 1 / 2, P <= 20), fused with the
+ * exchange of the similarity.  Rank r owns the genes [r * per, (r + 1) * per) (per % 256 == 0).  The unordered pairs of
+ * 128-gene blocks are dealt out over the ranks; the rank that gets a pair forms its correlation tile once and uses it for
+ * both gene sets: column sums for its own genes, row sums for the other block's genes, and the transformed similarity
+ * stored transposed into its own rows and directly into the row owner's rows -- peer_sim[q] is rank q's per x n
+ * similarity / adjacency block (peer-mapped for q != rank, b200w_ipc_open): half the MMAs and power chains of
+ * b200w_dev_sweep_similarity on a column block.  d_kpart (P x n) receives this rank's PARTIAL connectivities of all
+ * genes; the caller sums them over the ranks (all-reduce) -- which is also the point after which every rank's
+ * similarity block is complete. */
+int b200w_dev_sweep_dist(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t n, const double* h_steps, int P,
+                         int net_type, int world, int rank, int64_t per, void* const* peer_sim /* host array */,
+                         double* d_kpart, int device, void* stream);
 /* statistics of k[P, ldk >= n] as described at b200w_soft_threshold_stats; d_stats P x (4 + 2 nb),
  * d_buckets P x b200w_sft_exp_buckets() x 2 */
 int b200w_dev_sft_stats(const double* d_k, int P, int64_t n, int64_t ldk, int nbreaks, double* d_stats,

@@ -1,6 +1,10 @@
 // Correlation side of the hot path: standardise, soft-threshold sweep, adjacency.
 // Reference arithmetic: np.corrcoef (numpy lib/_function_base_impl.py cov/corrcoef) as called at
 // PyWGCNA/wgcna.py:882 and :1097; sweep wgcna.py:884-916; adjacency wgcna.py:1102-1111.
+#include <map>
+#include <mutex>
+#include <vector>
+
 #include "gemm_f64.cuh"
 #include "sweep_common.cuh"
 
@@ -422,6 +426,38 @@ __global__ void sweep_reduce_sym_kernel(const double* __restrict__ partial, cons
   k[(int64_t)p * n + j] = s - 1.0;
 }
 
+// sharded symmetric schedule (b200w_dev_sweep_dist): this rank's PARTIAL connectivities of ALL genes --
+//   own genes:   the column slots of their column tile (CTAs in list order) - 1        (wgcna.py:915)
+//   every gene:  + the row slots of the listed tiles whose row block holds it (CSR row_off / row_idx)
+// -- the caller sums the partial vectors of the ranks (all-reduce).  Fixed order, no atomics.
+__global__ void __launch_bounds__(128)
+sweep_reduce_dist_kernel(const double* __restrict__ partial, const double* __restrict__ rowpart,
+                         const int2* __restrict__ list, const int* __restrict__ cstart,
+                         const int* __restrict__ row_off, const int* __restrict__ row_idx, int G, int max_seg, int P,
+                         int64_t T, int64_t n, int64_t col0, int64_t ncols, double* __restrict__ kpart) {
+  const int64_t I = blockIdx.x;
+  const int local = threadIdx.x, p = blockIdx.y;
+  const int64_t j = I * 128 + local;
+  if (j >= n) return;
+  double s = 0.0;
+  if (j >= col0 && j < col0 + ncols) {
+    const int64_t jt = (j - col0) / kSweepBN;
+    const int col = (int)((j - col0) % kSweepBN);
+    const int64_t lo = cstart[jt], hi = cstart[jt + 1];
+    for (int64_t b = lo * G / T; b < G; ++b) {
+      int64_t t0, t1;
+      sweep_range(T, G, b, t0, t1);
+      if (t0 >= hi) break;
+      if (t1 <= lo || t0 >= t1) continue;
+      const int64_t seg = jt - list[t0].y;
+      s += partial[(((int64_t)b * max_seg + seg) * P + p) * kSweepBN + col];
+    }
+    s -= 1.0;
+  }
+  for (int q = row_off[I]; q < row_off[I + 1]; ++q) s += rowpart[((int64_t)row_idx[q] * P + p) * 128 + local];
+  kpart[(int64_t)p * n + j] = s;
+}
+
 // -------------------------------------------------------------------------------------------
 // K1 + K3  adjacency: correlation tile on the DMMA pipe, epilogue clip -> transform -> s ** power
 // (wgcna.py:1097-1111).  Rows of a NaN gene are NaN, as np.corrcoef makes them; the diagonal is not
@@ -734,7 +770,7 @@ static int sweep_impl(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t
     // the whole power reached so far (pow() with a large exponent: the value the reference's chain
     // approximates to ~1e-15).
     const int Pc = (P - p0 < kSweepMaxP) ? P - p0 : kSweepMaxP;
-    SweepParams prm;
+    SweepParams prm = {};
     prm.Z = dZ; prm.bad = d_bad; prm.n = n; prm.ldk = ldk; prm.col0 = col0; prm.ncols = ncols;
     prm.RT = RT; prm.P = Pc; prm.net_type = net_type;
     prm.sim = (p0 == 0) ? d_sim : nullptr;  // one launch writes it
@@ -848,5 +884,125 @@ static int adjacency_impl(const double* dZ, const uint8_t* d_bad, int64_t m, int
                                                                   net_type, power, ipower, d_power, row0,
                                                                   nrows, symmetric, col_tiles, dA);
   B200W_LAUNCHED();
+  return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Sharded SYMMETRIC sweep (multi-GPU): the unordered pairs of 128-gene blocks are dealt out over the ranks -- pair {a, b}
+// goes to the owner of a if a + b is even, else to the owner of b -- and the rank that gets a pair computes it ONCE, as the
+// tile (rows = the other block, columns = its own block): column sums for its own genes, row sums for the genes of the
+// other block, the similarity transposed into its own rows and directly into the row owner's rows over NVLink.  Half the
+// MMAs and half the power chains of the column-block schedule; the ranks' partial connectivities are summed by the caller.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct DistPlan {
+  int2* d_list = nullptr;
+  int *d_cstart = nullptr, *d_row_off = nullptr, *d_row_idx = nullptr;
+  std::vector<int2> list;
+  int T = 0;
+};
+std::map<std::vector<int64_t>, DistPlan> g_dist_plans;
+std::mutex g_dist_mu;
+}  // namespace
+
+extern "C" int b200w_dev_sweep_dist(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t n, const double* h_steps,
+                                    int P, int net_type, int world, int rank, int64_t per, void* const* peer_sim,
+                                    double* d_kpart, int device, void* stream) {
+  if (!dZ || !d_bad || !h_steps || !d_kpart || !peer_sim || P < 1 || n < 1 || world < 2 || world > 8 || rank < 0 ||
+      rank >= world || per < 256 || per % 256)
+    return fail(B200W_E_INVALID, "sweep_dist: bad args");
+  if (net_type < 0 || net_type > 2) return fail(B200W_E_INVALID, "sweep_dist: bad network type");
+  if (P > kSweepMaxP) return fail(B200W_E_UNSUPPORTED, "sweep_dist: at most %d powers", kSweepMaxP);
+  if (!corr_i8_enabled(m, n)) return fail(B200W_E_UNSUPPORTED, "sweep_dist: needs the tcgen05 correlation engine");
+  if (int e = ensure_device(device)) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  SweepParams prm = {};
+  for (int q = 0; q < kSweepMaxP; ++q) { prm.step[q] = 1.0; prm.istep[q] = 1; }
+  for (int q = 0; q < P; ++q) {
+    const double s = h_steps[q];
+    prm.step[q] = s;
+    prm.istep[q] = (s == 1.0) ? 1 : (s == 2.0 ? 2 : 0);
+    if (!prm.istep[q]) return fail(B200W_E_UNSUPPORTED, "sweep_dist: power steps must be 1 or 2");
+  }
+  const int64_t col0 = (int64_t)rank * per;
+  const int64_t ncols = col0 >= n ? 0 : (col0 + per <= n ? per : n - col0);
+  const int64_t B = (n + 127) / 128, CT = (ncols + kSweepBN - 1) / kSweepBN;
+  int sms = 0;
+  B200W_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  std::lock_guard<std::mutex> lk(g_dist_mu);
+  DistPlan& plan = g_dist_plans[{(int64_t)device, n, (int64_t)world, (int64_t)rank, per}];
+  if (plan.d_cstart == nullptr) {
+    auto owner = [&](int64_t blk) { return (blk * 128) / per; };
+    std::vector<int> cstart(CT + 1, 0);
+    for (int64_t jt = 0; jt < CT; ++jt) {
+      cstart[jt] = (int)plan.list.size();
+      const int64_t gb = (col0 + jt * kSweepBN) / 128;
+      for (int64_t a = 0; a < B; ++a) {
+        bool mine;
+        if (a == gb) mine = true;
+        else if (owner(a) == rank) mine = a < gb;  // a pair of two own blocks: once, in the upper orientation
+        else {
+          const int64_t lo = a < gb ? a : gb, hi = a < gb ? gb : a;
+          mine = (((lo + hi) & 1) == 0 ? owner(lo) : owner(hi)) == rank;
+        }
+        if (mine) plan.list.push_back(make_int2((int)a, (int)jt));
+      }
+    }
+    cstart[CT] = (int)plan.list.size();
+    plan.T = (int)plan.list.size();
+    std::vector<int> row_off(B + 1, 0), row_idx;
+    for (int64_t a = 0; a < B; ++a) {
+      row_off[a] = (int)row_idx.size();
+      for (int t = 0; t < plan.T; ++t)
+        if (plan.list[t].x == a && a != (col0 + (int64_t)plan.list[t].y * kSweepBN) / 128) row_idx.push_back(t);
+    }
+    row_off[B] = (int)row_idx.size();
+    B200W_CUDA(cudaMalloc(&plan.d_list, (plan.list.size() + 1) * sizeof(int2)));
+    B200W_CUDA(cudaMalloc(&plan.d_cstart, cstart.size() * sizeof(int)));
+    B200W_CUDA(cudaMalloc(&plan.d_row_off, row_off.size() * sizeof(int)));
+    B200W_CUDA(cudaMalloc(&plan.d_row_idx, (row_idx.size() + 1) * sizeof(int)));
+    B200W_CUDA(cudaMemcpy(plan.d_list, plan.list.data(), plan.list.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    B200W_CUDA(cudaMemcpy(plan.d_cstart, cstart.data(), cstart.size() * sizeof(int), cudaMemcpyHostToDevice));
+    B200W_CUDA(cudaMemcpy(plan.d_row_off, row_off.data(), row_off.size() * sizeof(int), cudaMemcpyHostToDevice));
+    B200W_CUDA(cudaMemcpy(plan.d_row_idx, row_idx.data(), row_idx.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  const int64_t T = plan.T;
+  Scratch part, rowpart;
+  int G = 1, max_seg = 1;
+  if (T > 0) {
+    G = (int)(T < sms ? T : sms);
+    for (int b = 0; b < G; ++b) {
+      int64_t t0, t1;
+      sweep_range(T, G, b, t0, t1);
+      if (t0 >= t1) continue;
+      const int seg = plan.list[t1 - 1].y - plan.list[t0].y + 1;
+      if (seg > max_seg) max_seg = seg;
+    }
+    prm.Z = dZ; prm.bad = d_bad; prm.n = n; prm.ldk = b200w_padded_k(m); prm.col0 = col0; prm.ncols = ncols;
+    prm.RT = B; prm.T = T; prm.P = P; prm.net_type = net_type; prm.simple_steps = 1; prm.max_seg = max_seg;
+    prm.symmetric = 0; prm.sim_transposed = 1; prm.dist = 1; prm.per_rows = per; prm.tile_list = plan.d_list;
+    prm.adj_power = 1.0; prm.adj_ipower = 1;
+    for (int r = 0; r < 8; ++r) prm.peer_sim[r] = r < world ? (double*)peer_sim[r] : nullptr;
+    prm.sim = (double*)peer_sim[rank];
+    if (!prm.sim) return fail(B200W_E_INVALID, "sweep_dist: peer_sim[rank] is NULL");
+    B200W_CUDA(part.alloc((size_t)G * max_seg * P * kSweepBN * sizeof(double), st));
+    B200W_CUDA(rowpart.alloc((size_t)T * P * 128 * sizeof(double), st));
+    prm.partial = part.as<double>();
+    prm.rowpart = rowpart.as<double>();
+    if (int e = sweep_i8_launch(prm, m, CT, P, G, device, st)) return e;
+  } else {
+    B200W_CUDA(part.alloc(16, st));
+    B200W_CUDA(rowpart.alloc(16, st));
+  }
+  if (T > 0) {
+    dim3 rgrid((unsigned)B, (unsigned)P);
+    sweep_reduce_dist_kernel<<<rgrid, 128, 0, st>>>(part.as<double>(), rowpart.as<double>(), plan.d_list, plan.d_cstart,
+                                                    plan.d_row_off, plan.d_row_idx, G, max_seg, P, T, n, col0, ncols,
+                                                    d_kpart);
+    B200W_LAUNCHED();
+  } else {
+    B200W_CUDA(cudaMemsetAsync(d_kpart, 0, (size_t)P * n * sizeof(double), st));
+  }
   return 0;
 }

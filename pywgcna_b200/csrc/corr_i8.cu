@@ -214,14 +214,20 @@ __device__ __forceinline__ double int_pow1(double s, int e) {
 struct TileWalk {
   int64_t t, t1, jt, it, RT;
   bool sym;
+  const int2* list;
   __device__ __forceinline__ void init(const SweepParams& prm) {
     int64_t t0;
     sweep_range(prm.T, gridDim.x, blockIdx.x, t0, t1);
     t = t0;
     sym = prm.symmetric != 0;
     RT = prm.RT;
+    list = prm.tile_list;
     if (t0 >= t1) return;
-    if (sym) {
+    if (list != nullptr) {
+      const int2 e = list[t0];
+      it = e.x;
+      jt = e.y;
+    } else if (sym) {
       jt = sym_col_of(t0);
       it = t0 - sym_offset(jt);
     } else {
@@ -232,6 +238,14 @@ struct TileWalk {
   __device__ __forceinline__ bool valid() const { return t < t1; }
   __device__ __forceinline__ void next() {
     ++t;
+    if (list != nullptr) {
+      if (t < t1) {
+        const int2 e = list[t];
+        it = e.x;
+        jt = e.y;
+      }
+      return;
+    }
     ++it;
     if (it >= (sym ? (jt >> 1) + 1 : RT)) { ++jt; it = 0; }
   }
@@ -395,7 +409,8 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
     for (; w.valid(); w.next(), ++tile_no) {
       const int64_t jt = w.jt, it = w.it, t = w.t;
       const int64_t j0 = prm.col0 + jt * kBN, i0 = it * kBM;
-      const bool two_pass = w.sym && it < (jt >> 1);  // strictly above the diagonal block
+      // a tile off the diagonal block serves the genes of its rows too (symmetric schedules)
+      const bool two_pass = prm.dist ? (it != ((prm.col0 + jt * kBN) >> 7)) : (w.sym && it < (jt >> 1));
       mark(4);
       tc::epi_barrier();  // every warp is done with bad_row, col_scale and the park of the previous tile
       if (jt != cur_jt) {
@@ -460,9 +475,16 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       const unsigned rbad_mask = __ballot_sync(0xffffffffu, bad_row[wm * 32 + lane] != 0);
       const unsigned cbad_mask = __ballot_sync(0xffffffffu, cbad);
       const unsigned rvalid_mask = rows_valid >= 32 ? 0xffffffffu : (rows_valid <= 0 ? 0u : ((1u << rows_valid) - 1u));
-      const bool write_direct = prm.sim != nullptr && !prm.sim_transposed && col_in;
+      // (sharded: the diagonal block is covered by the transposed stores of its two column tiles)
+      const bool write_direct = prm.sim != nullptr && (prm.dist ? two_pass : !prm.sim_transposed) && col_in;
       const bool keep_out = prm.sim != nullptr && prm.sim_transposed;
       double* out_ptr = prm.sim != nullptr ? prm.sim + row_base * n + gj : nullptr;
+      if (prm.dist && prm.sim != nullptr) {
+        // the tile's 128 rows belong to one rank (row blocks start on 256-row boundaries): element (gi, gj) goes into
+        // that rank's block -- its own HBM or a peer's over NVLink
+        const int64_t owner = i0 / prm.per_rows;
+        out_ptr = prm.peer_sim[owner] + (row_base - owner * prm.per_rows) * n + gj;
+      }
       const int net_type = prm.net_type;
 
       // similarity of one element (wgcna.py:884-889 / :1102-1107) and what goes out with prm.sim: the similarity
@@ -518,7 +540,7 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
           if (prm.sim != nullptr) {
             const double s_out = nan_pair ? qnan : out_value(sv);
             if (keep_out) my[r * kWarpPitch + lane] = s_out;  // stored by the transposed pass below
-            else if (write_direct && valid) out_ptr[(int64_t)r * n] = s_out;
+            if (write_direct && valid) out_ptr[(int64_t)r * n] = s_out;
           }
           // chain start: the diagonal counts as 1 even for a NaN gene (wgcna.py:897), NaN pairs are skipped by
           // nansum (:915), rows past the matrix contribute nothing
@@ -543,6 +565,17 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       }
       }
       mark(3);  // first pass
+      if (prm.sim != nullptr && prm.sim_transposed) {  // lane <-> row of the sub-tile: 256-byte row segments
+        // (before the second pass: its row-sum exchange reuses the parked tile)
+        __syncwarp();
+        const int64_t gi = i0 + wm * 32 + lane;
+#pragma unroll 1
+        for (int c = 0; c < 32; ++c) {
+          const int64_t gjc = j0 + wn * 32 + c;
+          if (gjc >= jend) break;  // warp-uniform
+          if (gi < n) prm.sim[(gjc - prm.col0) * n + gi] = my[lane * kWarpPitch + c];
+        }
+      }
       if (two_pass) {
         // lane <-> row: row sums over the warp's 32 columns, eight at a time, for the genes of the tile's rows
         // (their column tiles never visit these rows), and the mirrored half of the output
@@ -555,7 +588,8 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
         const int64_t col_base = j0 + wn * 32;
         const int cols_valid = (int)((jend - col_base) < 32 ? (jend - col_base) : 32);
         const unsigned cvalid_mask = cols_valid >= 32 ? 0xffffffffu : (cols_valid <= 0 ? 0u : ((1u << cols_valid) - 1u));
-        double* mir_ptr = prm.sim != nullptr ? prm.sim + col_base * n + gi : nullptr;
+        // (sharded: both orientations are already written by the first pass and the transposed pass)
+        double* mir_ptr = (prm.sim != nullptr && !prm.dist) ? prm.sim + col_base * n + gi : nullptr;
         __syncwarp();
 #pragma unroll 1
         for (int h0 = 0; h0 < 32; h0 += 16) {
@@ -568,10 +602,11 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const int cx = c0 + u;
-            double sv = similarity(pre[g8 + u]);
+            // (with keep_out the first pass has left the similarity itself in the tile, NaN for NaN pairs)
+            double sv = keep_out ? pre[g8 + u] : similarity(pre[g8 + u]);
             const bool nan_pair = rbad || ((cbad_mask >> cx) & 1u);
             const bool inside = row_in && ((cvalid_mask >> cx) & 1u);
-            if (prm.sim != nullptr && inside) mir_ptr[(int64_t)cx * n] = nan_pair ? qnan : out_value(sv);
+            if (mir_ptr != nullptr && inside) mir_ptr[(int64_t)cx * n] = nan_pair ? qnan : out_value(sv);
             double c0v = 1.0;
             if (nan_pair || !inside) { sv = 0.0; c0v = 0.0; }
             s1[u] = sv;
@@ -598,16 +633,6 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
             double* dst = prm.rowpart + t * P * kBM;
             for (int p = 0; p < P; ++p) dst[p * kBM + row] = park[p * kBM + row] + park[(P + p) * kBM + row];
           }
-        }
-      }
-      if (prm.sim != nullptr && prm.sim_transposed) {  // lane <-> row of the sub-tile: 256-byte row segments
-        __syncwarp();
-        const int64_t gi = i0 + wm * 32 + lane;
-#pragma unroll 1
-        for (int c = 0; c < 32; ++c) {
-          const int64_t gjc = j0 + wn * 32 + c;
-          if (gjc >= jend) break;  // warp-uniform
-          if (gi < n) prm.sim[(gjc - prm.col0) * n + gi] = my[lane * kWarpPitch + c];
         }
       }
     }

@@ -32,6 +32,15 @@ struct SweepParams {
   const double* d_adj_power;  // optional: the power in device memory (device-side selection)
   const double* zscale;       // per gene 2^(e - 46): Z = digits * zscale
   long long* debug;           // optional (B200W_CORR_DEBUG=1): [CTA][8] cycles per phase of epilogue warp 0 / the MMA warp
+  // sharded symmetric schedule (tcgen05 engine, b200w_dev_sweep_dist): the tiles of this rank as an explicit list
+  // (x = 128-row block, y = 64-column tile of the rank's column block), column-major; every tile off the diagonal block
+  // serves two gene sets -- column sums for the rank's own genes, row sums for the genes of its rows (any rank's) --
+  // and its similarity goes to BOTH owners: transposed into the rank's own rows, directly into the row owner's block
+  // (peer_sim[owner], peer-mapped HBM) from inside the kernel
+  const int2* tile_list;
+  double* peer_sim[8];
+  int64_t per_rows;
+  int dist;
 };
 
 __host__ __device__ __forceinline__ void sweep_range(int64_t T, int64_t G, int64_t b, int64_t& t0, int64_t& t1) {

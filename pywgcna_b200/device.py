@@ -148,6 +148,8 @@ class DeviceNetwork:
         # peer); "gather" = NCCL all-gathers before the kernel starts
         self.pull = (self.fused and bool(self.use_dist)
                      and os.environ.get("B200WGCNA_EXCHANGE", "pull") == "pull")
+        self._A_raw = None
+        self._peer_A_ptrs = None
         self._op_raw = None
         self._peer_op_ptrs = None
         self._epoch = 0
@@ -159,6 +161,12 @@ class DeviceNetwork:
         if keep_similarity is None:
             keep_similarity = os.environ.get("B200WGCNA_KEEP_SIMILARITY", "1") != "0"
         self.keep_similarity = bool(keep_similarity)
+        # sweep of the sharded run: "symmetric" = block pairs dealt out over the ranks, every correlation tile formed
+        # once and its similarity stored into both owners' blocks from inside the kernel (b200w_dev_sweep_dist);
+        # "full" = every rank sweeps its whole column block
+        self.sym_sweep = (self.world > 1 and bool(self.use_dist) and self.keep_similarity
+                          and os.environ.get("B200WGCNA_SWEEP_DIST", "symmetric") != "full")
+        self._sync_token = None
         self.T = None
         self._T_raw = None
         self._peer_ptrs = None
@@ -174,6 +182,8 @@ class DeviceNetwork:
                 self.lib.b200w_dev_free(self._T_raw, self.device)
             if self._op_raw:
                 self.lib.b200w_dev_free(self._op_raw, self.device)
+            if self._A_raw:
+                self.lib.b200w_dev_free(self._A_raw, self.device)
         except Exception:
             pass
 
@@ -186,6 +196,19 @@ class DeviceNetwork:
                       self._stream()))
         self._standardized = True
         self._sim_in_A = False
+
+    def _alloc_A(self):
+        """This rank's rows of the similarity / adjacency.  With the symmetric sharded sweep the block lives in a
+        cudaMalloc buffer of ``per`` rows that the peers map through CUDA IPC (they store into it)."""
+        if self.A is not None:
+            return
+        if self.sym_sweep:
+            p = C.c_void_p()
+            L.check(self.lib.b200w_dev_malloc(self.per * self.n * 8, self.device, C.byref(p)))
+            self._A_raw = p.value
+            self.A = torch.as_tensor(_DevView(p.value, (self.per, self.n)), device=self.dev)
+        else:
+            self.A = torch.empty((max(self.nrows, 1), self.n), dtype=torch.float64, device=self.dev)
 
     def _all_gather_rows(self, full: torch.Tensor):
         """In-place all-gather of the ``per``-row blocks of ``full`` ([op_rows, ...], contiguous)."""
@@ -201,14 +224,35 @@ class DeviceNetwork:
         powers = np.sort(np.asarray(powers, dtype=np.float64))
         steps = np.ascontiguousarray(np.diff(np.concatenate(([0.0], powers))))
         P = len(powers)
+        if self.sym_sweep and P <= 20 and bool(np.all((steps == 1.0) | (steps == 2.0))):
+            import torch.distributed as dist
+
+            self._alloc_A()
+            if self._peer_ptrs is None:
+                self.connect_peers()
+            kpart = torch.empty((P, self.n), dtype=torch.float64, device=self.dev)
+            # the peers' kernels store into this rank's block: nobody starts before every rank is through with what
+            # it still reads out of the block (the TOM epilogue of the previous pass) -- a stream-ordered collective
+            if self._sync_token is None:
+                self._sync_token = torch.zeros(1, dtype=torch.float32, device=self.dev)
+            dist.all_reduce(self._sync_token, group=self.group)
+            rc = self.lib.b200w_dev_sweep_dist(self.Z.data_ptr(), self.bad.data_ptr(), self.m, self.n,
+                                               steps.ctypes.data, P, self.net, self.world, self.rank, self.per,
+                                               self._peer_A_ptrs, kpart.data_ptr(), self.device, self._stream())
+            if rc != L.E_UNSUPPORTED:  # (the FP64 correlation engine has no sharded schedule: the column-block path)
+                L.check(rc)
+                # the sum of the ranks' partial connectivities; once it has passed, every rank's kernel has finished,
+                # so the similarity rows the peers stored into this rank's block are complete as well
+                dist.all_reduce(kpart, group=self.group)
+                self._sim_in_A = True
+                return kpart
         col0, ncols = (0, self.n) if self.world == 1 else (self.row0, self.nrows)
         kloc = torch.empty((P, max(ncols, 1)), dtype=torch.float64, device=self.dev)
         if ncols > 0 and self.keep_similarity:
             # the sweep also writes this rank's rows of the transformed similarity into the adjacency buffer,
             # and adjacency() of the same data finishes them with an elementwise S ** power instead of forming
             # the correlation a second time as the reference does (wgcna.py:882 and :1097)
-            if self.A is None:
-                self.A = torch.empty((max(self.nrows, 1), self.n), dtype=torch.float64, device=self.dev)
+            self._alloc_A()
             L.check(self.lib.b200w_dev_sweep_similarity(self.Z.data_ptr(), self.bad.data_ptr(), self.m, self.n,
                                                         steps.ctypes.data, P, self.net, col0, ncols,
                                                         kloc.data_ptr(), self.A.data_ptr(), self.device,
@@ -277,8 +321,7 @@ class DeviceNetwork:
         or the device scalar ``sft()`` returned (then the kernels read it from HBM: no host round trip)."""
         if not self._standardized:
             self.standardize()
-        if self.A is None:
-            self.A = torch.empty((max(self.nrows, 1), self.n), dtype=torch.float64, device=self.dev)
+        self._alloc_A()
         on_dev = isinstance(power, torch.Tensor) and power.is_cuda
         if on_dev:
             assert power.dtype == torch.float64 and power.device == self.dev
@@ -356,16 +399,20 @@ class DeviceNetwork:
             import torch.distributed as dist
 
             self._operand()
-            handles = self.ipc_handle() + (self.ipc_handle(self._op_raw) if self.pull else bytes(64))
+            if self.sym_sweep:
+                self._alloc_A()
+            handles = (self.ipc_handle() + (self.ipc_handle(self._op_raw) if self.pull else bytes(64))
+                       + (self.ipc_handle(self._A_raw) if self.sym_sweep else bytes(64)))
             mine = torch.frombuffer(bytearray(handles), dtype=torch.uint8).to(self.dev)
-            allh = torch.zeros((self.world, 128), dtype=torch.uint8, device=self.dev)
+            allh = torch.zeros((self.world, 192), dtype=torch.uint8, device=self.dev)
             dist.all_gather_into_tensor(allh, mine, group=self.group)
             allh = allh.cpu().numpy()
-            ptrs, op_ptrs = [], []
+            ptrs, op_ptrs, a_ptrs = [], [], []
             for r in range(self.world):
                 if r == self.rank:
                     ptrs.append(self._T_raw)
                     op_ptrs.append(self._op_raw or 0)
+                    a_ptrs.append(self._A_raw or 0)
                     continue
                 p = C.c_void_p()
                 L.check(self.lib.b200w_ipc_open(allh[r, :64].tobytes(), self.device, C.byref(p)))
@@ -373,11 +420,18 @@ class DeviceNetwork:
                 ptrs.append(p.value)
                 if self.pull:
                     q = C.c_void_p()
-                    L.check(self.lib.b200w_ipc_open(allh[r, 64:].tobytes(), self.device, C.byref(q)))
+                    L.check(self.lib.b200w_ipc_open(allh[r, 64:128].tobytes(), self.device, C.byref(q)))
                     self._peer_open.append(q.value)
                     op_ptrs.append(q.value)
+                if self.sym_sweep:
+                    q = C.c_void_p()
+                    L.check(self.lib.b200w_ipc_open(allh[r, 128:].tobytes(), self.device, C.byref(q)))
+                    self._peer_open.append(q.value)
+                    a_ptrs.append(q.value)
             if self.pull:
                 self._peer_op_ptrs = (C.c_void_p * self.world)(*[int(p) for p in op_ptrs])
+            if self.sym_sweep:
+                self._peer_A_ptrs = (C.c_void_p * self.world)(*[int(p) for p in a_ptrs])
         self._peer_ptrs = (C.c_void_p * self.world)(*[int(p) for p in ptrs])
 
     def tom_prepare(self, A_rows: torch.Tensor | None = None):
