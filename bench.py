@@ -373,6 +373,8 @@ def measure_ours(args, wl, steps, warmup, world, rank, local, with_e2e, with_fas
     X_np = make_expression(m, n, F=F, seed=seed)
     X_host = torch.from_numpy(X_np).pin_memory()
     net_dev = DeviceNetwork(X_host, device=local, networkType=net, precision=args.precision, world=world, rank=rank)
+    # schedule of the soft-threshold sweep over the ranks (device.py: sym_sweep); None on one GPU
+    sharded_sweep = None if world == 1 else ("symmetric" if net_dev.sym_sweep else "full")
     prec_name = {L.PREC_F64: "f64", L.PREC_I8: "i8"}[
         L.PREC_F64 if lib.b200w_tom_operand_bytes(128, net_dev.prec) == 128 * 128 * 8 else L.PREC_I8]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -574,7 +576,7 @@ def measure_ours(args, wl, steps, warmup, world, rank, local, with_e2e, with_fas
     return {"ms_per_step": ms_step, "value": step_flops(m, n, P) / ms_step / 1e9, "phases_ms": phases,
             "roofline": roofline, "e2e": e2e, "e2e_fused": e2e_fused, "clocks": clocks, "gpu_launches": int(launches),
             "selected_power": power, "tom_precision": prec_name, "parity": parity, "steps": steps,
-            "warmup": max(warmup, 3),
+            "warmup": max(warmup, 3), "sharded_sweep": sharded_sweep,
             "dtype": "f64" if prec_name == "f64" else "f64 (DMMA) + s8->s32 digit slices (tcgen05)"}
 
 
@@ -615,6 +617,7 @@ def run_ours(args):
             "dtype": r["dtype"], "data": "synthetic", "config": config_of(wl, world),
             "selected_power": r["selected_power"], "tom_precision": r["tom_precision"],
             "clocks": r["clocks"], "gpu_launches": r["gpu_launches"], "phases_ms": r["phases_ms"],
+            "sharded_sweep": r["sharded_sweep"],
             "parity": r["parity"], "roofline": r["roofline"], "cpu_baseline": cpu, "e2e": r["e2e"],
             "e2e_fused": r["e2e_fused"], "secondary": sec,
         }

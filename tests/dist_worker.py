@@ -7,7 +7,9 @@ tcgen05 kernel, copy-engine pulls of the digit planes gated per plane) and compa
   * with the float64 numpy restatement of the reference (oracle/restated.py): 1e-10,
   * k of the sweep, the selected power and the adjacency blocks likewise,
 
-for both exchange modes ("pull", "gather") and for sizes that leave the last rank short or empty.
+for both exchange modes ("pull", "gather"), both schedules of the sharded sweep ("symmetric": block pairs dealt out over
+the ranks, similarity stored into the peers' blocks from inside the kernel; "full": column blocks) and for sizes that
+leave the last rank short or empty.
 Prints one JSON line on rank 0; exit code 0 only if every comparison held.
 """
 import json
@@ -37,8 +39,10 @@ def main():
     for n in sizes:
         X = make_expression(48, n, F=5, seed=1000 + n)
         X[:, 7] = 3.25  # a constant gene: NaN row / column in the correlation, zeroed by the TOM
-        for mode in ("pull", "gather"):
+        # operand exchange of the TOM x schedule of the sharded sweep (device.py: sym_sweep)
+        for mode, sweep_mode in (("pull", "symmetric"), ("gather", "symmetric"), ("pull", "full"), ("gather", "full")):
             os.environ["B200WGCNA_EXCHANGE"] = mode
+            os.environ["B200WGCNA_SWEEP_DIST"] = sweep_mode
             net = DeviceNetwork(X, device=local, networkType="signed hybrid")
             for rep in range(2):  # twice: the second pass reuses buffers, epochs and peer mappings
                 power, tab = net.sft(powers)
@@ -66,7 +70,7 @@ def main():
                 Td, Ad = full_T[:n].cpu().numpy(), full_A[:n].cpu().numpy()
                 A_ref = O.adjacency(X, adjacencyType="signed hybrid", power=p_dist)
                 T_ref = O.TOMsimilarity(A_ref.copy(), TOMType="signed").to_numpy()
-                rec = {"n": n, "mode": mode, "world": world, "per": per, "power": p_dist,
+                rec = {"n": n, "mode": mode, "sweep": sweep_mode, "world": world, "per": per, "power": p_dist,
                        "power_equal": p_dist == float(p1),
                        "k_bitwise": bool(np.array_equal(k_dist, k1)),
                        "k_max_abs": float(np.abs(k_dist - k1).max()),
