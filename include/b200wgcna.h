@@ -229,6 +229,10 @@ int b200w_dev_adjacency_from_similarity(double* d_sim_inout /* nrows x n */, int
 int b200w_dev_sweep_dist(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t n, const double* h_steps, int P,
                          int net_type, int world, int rank, int64_t per, void* const* peer_sim /* host array */,
                          double* d_kpart, int device, void* stream);
+/* Host only (no device): the tile list of b200w_dev_sweep_dist for one rank as (128-row block, 64-column tile of the
+ * rank's column block) pairs, in launch order.  Returns the number of tiles (-1: bad arguments) and writes them to
+ * out_xy[2 * count] when capacity suffices.  For tests of the schedule: over the ranks every pair of blocks exactly once. */
+int64_t b200w_sweep_dist_tiles(int64_t n, int world, int rank, int64_t per, int32_t* out_xy, int64_t capacity);
 /* statistics of k[P, ldk >= n] as described at b200w_soft_threshold_stats; d_stats P x (4 + 2 nb),
  * d_buckets P x b200w_sft_exp_buckets() x 2 */
 int b200w_dev_sft_stats(const double* d_k, int P, int64_t n, int64_t ldk, int nbreaks, double* d_stats,

@@ -904,7 +904,49 @@ struct DistPlan {
 };
 std::map<std::vector<int64_t>, DistPlan> g_dist_plans;
 std::mutex g_dist_mu;
+
+// The tiles of one rank, column-major: x = 128-row block, y = 64-column tile of the rank's column block;
+// cstart[jt] .. cstart[jt + 1] = the tiles of column tile jt.
+void dist_tile_list(int64_t n, int world, int rank, int64_t per, std::vector<int2>& list, std::vector<int>& cstart) {
+  const int64_t col0 = (int64_t)rank * per;
+  const int64_t ncols = col0 >= n ? 0 : (col0 + per <= n ? per : n - col0);
+  const int64_t B = (n + 127) / 128, CT = (ncols + kSweepBN - 1) / kSweepBN;
+  auto owner = [&](int64_t blk) { return (blk * 128) / per; };
+  cstart.assign(CT + 1, 0);
+  list.clear();
+  for (int64_t jt = 0; jt < CT; ++jt) {
+    cstart[jt] = (int)list.size();
+    const int64_t gb = (col0 + jt * kSweepBN) / 128;
+    for (int64_t a = 0; a < B; ++a) {
+      bool mine;
+      if (a == gb) mine = true;
+      else if (owner(a) == rank) mine = a < gb;  // a pair of two own blocks: once, in the upper orientation
+      else {
+        const int64_t lo = a < gb ? a : gb, hi = a < gb ? gb : a;
+        mine = (((lo + hi) & 1) == 0 ? owner(lo) : owner(hi)) == rank;
+      }
+      if (mine) list.push_back(make_int2((int)a, (int)jt));
+    }
+  }
+  cstart[CT] = (int)list.size();
+}
 }  // namespace
+
+// Host only (no device needed): the tile list of b200w_dev_sweep_dist for one rank, as (row block, column tile) pairs.
+// Returns the number of tiles; writes them when capacity suffices.  For tests of the schedule.
+extern "C" int64_t b200w_sweep_dist_tiles(int64_t n, int world, int rank, int64_t per, int32_t* out_xy,
+                                          int64_t capacity) {
+  if (n < 1 || world < 2 || world > 8 || rank < 0 || rank >= world || per < 256 || per % 256) return -1;
+  std::vector<int2> list;
+  std::vector<int> cstart;
+  dist_tile_list(n, world, rank, per, list, cstart);
+  if (out_xy != nullptr && capacity >= (int64_t)list.size())
+    for (size_t t = 0; t < list.size(); ++t) {
+      out_xy[2 * t] = list[t].x;
+      out_xy[2 * t + 1] = list[t].y;
+    }
+  return (int64_t)list.size();
+}
 
 extern "C" int b200w_dev_sweep_dist(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t n, const double* h_steps,
                                     int P, int net_type, int world, int rank, int64_t per, void* const* peer_sim,
@@ -933,23 +975,8 @@ extern "C" int b200w_dev_sweep_dist(const double* dZ, const uint8_t* d_bad, int6
   std::lock_guard<std::mutex> lk(g_dist_mu);
   DistPlan& plan = g_dist_plans[{(int64_t)device, n, (int64_t)world, (int64_t)rank, per}];
   if (plan.d_cstart == nullptr) {
-    auto owner = [&](int64_t blk) { return (blk * 128) / per; };
-    std::vector<int> cstart(CT + 1, 0);
-    for (int64_t jt = 0; jt < CT; ++jt) {
-      cstart[jt] = (int)plan.list.size();
-      const int64_t gb = (col0 + jt * kSweepBN) / 128;
-      for (int64_t a = 0; a < B; ++a) {
-        bool mine;
-        if (a == gb) mine = true;
-        else if (owner(a) == rank) mine = a < gb;  // a pair of two own blocks: once, in the upper orientation
-        else {
-          const int64_t lo = a < gb ? a : gb, hi = a < gb ? gb : a;
-          mine = (((lo + hi) & 1) == 0 ? owner(lo) : owner(hi)) == rank;
-        }
-        if (mine) plan.list.push_back(make_int2((int)a, (int)jt));
-      }
-    }
-    cstart[CT] = (int)plan.list.size();
+    std::vector<int> cstart;
+    dist_tile_list(n, world, rank, per, plan.list, cstart);
     plan.T = (int)plan.list.size();
     std::vector<int> row_off(B + 1, 0), row_idx;
     for (int64_t a = 0; a < B; ++a) {

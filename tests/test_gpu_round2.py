@@ -179,8 +179,9 @@ def _free_port():
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_ranks_real_nccl_and_ipc(gpu, world):
     """`world` processes, one per GPU (tests/dist_worker.py): the union of the ranks' TOM blocks is bit-identical
-    to the single-GPU result and within 1e-10 of the float64 oracle, for both exchange modes and for sizes that
-    leave the last rank short (600) or empty (200).  Skipped when fewer GPUs are visible."""
+    to the single-GPU result and within 1e-10 of the float64 oracle, for both exchange modes of the TOM operand, both
+    schedules of the sharded sweep (symmetric with peer stores / column blocks) and for sizes that leave the last rank
+    short (600) or empty (200).  Skipped when fewer GPUs are visible."""
     import json
     import subprocess
     import sys
@@ -194,7 +195,9 @@ def test_ranks_real_nccl_and_ipc(gpu, world):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=root)
     assert out.returncode == 0, (out.stdout[-3000:], out.stderr[-3000:])
     rep = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
-    assert rep["ok"] and len(rep["cases"]) == 8
+    assert rep["ok"] and len(rep["cases"]) == 16  # 4 sizes x (pull, gather) x (symmetric, full)
+    assert {(c["mode"], c["sweep"]) for c in rep["cases"]} == {(e, s) for e in ("pull", "gather")
+                                                               for s in ("symmetric", "full")}
     for c in rep["cases"]:
         assert c["tom_bitwise"] and c["adj_bitwise"] and c["power_equal"], c
 

@@ -206,3 +206,48 @@ def test_install_rebinds_the_real_reference_class():
         assert Wm.linkage is link
     finally:
         bw.uninstall(Wm.WGCNA)
+
+
+@pytest.mark.parametrize("n,world", [(2304, 2), (2500, 4), (600, 2), (200, 4), (5000, 8), (3001, 3)])
+def test_sharded_symmetric_sweep_schedule_covers_every_block_pair_once(n, world):
+    """Tile lists of b200w_dev_sweep_dist (corr.cu): over the ranks, every unordered pair of 128-gene blocks is formed
+    exactly once -- as (rows = one block, both 64-column tiles of the other block) on the rank that owns the column
+    block -- and every diagonal block once on its owner; the tiles are balanced over the ranks that have genes."""
+    from pywgcna_b200 import _lib as L
+    from pywgcna_b200.device import ALIGN, rows_per_rank
+
+    lib = L.load()
+    per = rows_per_rank(n, world, ALIGN)
+    B = -(-n // 128)
+    seen = {}
+    counts = []
+    for rank in range(world):
+        cnt = lib.b200w_sweep_dist_tiles(n, world, rank, per, None, 0)
+        assert cnt >= 0
+        xy = np.zeros((max(cnt, 1), 2), dtype=np.int32)
+        assert lib.b200w_sweep_dist_tiles(n, world, rank, per, xy.ctypes.data, cnt) == cnt
+        counts.append(cnt)
+        col0 = rank * per
+        last = (-1, -1)
+        for a, jt in xy[:cnt]:
+            assert (jt, a) > last  # column-major, rows ascending
+            last = (jt, a)
+            j0 = col0 + int(jt) * 64
+            assert j0 < min(n, col0 + per) and 0 <= a < B
+            key = (int(a), j0 // 64)  # (row block, global 64-column tile)
+            assert key not in seen
+            seen[key] = rank
+    for a in range(B):
+        for b in range(a, B):
+            tiles_b = [c for c in (2 * b, 2 * b + 1) if c * 64 < n]  # a as rows, b's column tiles
+            tiles_a = [c for c in (2 * a, 2 * a + 1) if c * 64 < n]
+            got_ab = [(a, c) in seen for c in tiles_b]
+            got_ba = [(b, c) in seen for c in tiles_a]
+            if a == b:
+                assert all(got_ab)
+            else:  # exactly one orientation, complete
+                assert (all(got_ab) and not any(got_ba)) or (all(got_ba) and not any(got_ab)), (a, b)
+    busy = [c for c, r in zip(counts, range(world)) if r * per + per <= n]  # ranks with a full block
+    if len(busy) > 1:
+        assert max(busy) - min(busy) <= 0.1 * max(busy) + 4
+    assert lib.b200w_sweep_dist_tiles(n, 1, 0, per, None, 0) == -1
