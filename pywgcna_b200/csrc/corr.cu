@@ -430,11 +430,20 @@ __global__ void sweep_reduce_sym_kernel(const double* __restrict__ partial, cons
 //   own genes:   the column slots of their column tile (CTAs in list order) - 1        (wgcna.py:915)
 //   every gene:  + the row slots of the listed tiles whose row block holds it (CSR row_off / row_idx)
 // -- the caller sums the partial vectors of the ranks (all-reduce).  Fixed order, no atomics.
+// Sharded symmetric sweep: this rank's partial connectivities of all genes.  The tile list comes in up to two parts
+// (launches): part q walks list[tb[q], tb[q] + Tq[q]) with Gq[q] CTAs, its column tile jt's run of the list is
+// cstart[q * (CT + 1) + jt ..]; row sums by the CSR (row_off, row_idx) over list positions.
+struct DistReduceParts {
+  const double* partial[2];
+  int64_t tb[2], T[2];
+  int G[2], max_seg[2];
+  int nparts;
+};
 __global__ void __launch_bounds__(128)
-sweep_reduce_dist_kernel(const double* __restrict__ partial, const double* __restrict__ rowpart,
+sweep_reduce_dist_kernel(const DistReduceParts parts, const double* __restrict__ rowpart,
                          const int2* __restrict__ list, const int* __restrict__ cstart,
-                         const int* __restrict__ row_off, const int* __restrict__ row_idx, int G, int max_seg, int P,
-                         int64_t T, int64_t n, int64_t col0, int64_t ncols, double* __restrict__ kpart) {
+                         const int* __restrict__ row_off, const int* __restrict__ row_idx, int P, int64_t n,
+                         int64_t col0, int64_t ncols, int CT, double* __restrict__ kpart) {
   const int64_t I = blockIdx.x;
   const int local = threadIdx.x, p = blockIdx.y;
   const int64_t j = I * 128 + local;
@@ -443,14 +452,21 @@ sweep_reduce_dist_kernel(const double* __restrict__ partial, const double* __res
   if (j >= col0 && j < col0 + ncols) {
     const int64_t jt = (j - col0) / kSweepBN;
     const int col = (int)((j - col0) % kSweepBN);
-    const int64_t lo = cstart[jt], hi = cstart[jt + 1];
-    for (int64_t b = lo * G / T; b < G; ++b) {
-      int64_t t0, t1;
-      sweep_range(T, G, b, t0, t1);
-      if (t0 >= hi) break;
-      if (t1 <= lo || t0 >= t1) continue;
-      const int64_t seg = jt - list[t0].y;
-      s += partial[(((int64_t)b * max_seg + seg) * P + p) * kSweepBN + col];
+    for (int q = 0; q < parts.nparts; ++q) {
+      const int64_t lo = cstart[q * (CT + 1) + jt], hi = cstart[q * (CT + 1) + jt + 1];
+      const int64_t T = parts.T[q], tb = parts.tb[q];
+      const int G = parts.G[q];
+      if (lo >= hi || T <= 0) continue;
+      for (int64_t b = (lo - tb) * G / T; b < G; ++b) {
+        int64_t t0, t1;
+        sweep_range(T, G, b, t0, t1);
+        t0 += tb;
+        t1 += tb;
+        if (t0 >= hi) break;
+        if (t1 <= lo || t0 >= t1) continue;
+        const int64_t seg = jt - list[t0].y;
+        s += parts.partial[q][(((int64_t)b * parts.max_seg[q] + seg) * P + p) * kSweepBN + col];
+      }
     }
     s -= 1.0;
   }
@@ -889,46 +905,100 @@ static int adjacency_impl(const double* dZ, const uint8_t* d_bad, int64_t m, int
 
 
 // ---------------------------------------------------------------------------------------------------------------
-// Sharded SYMMETRIC sweep (multi-GPU): the unordered pairs of 128-gene blocks are dealt out over the ranks -- pair {a, b}
-// goes to the owner of a if a + b is even, else to the owner of b -- and the rank that gets a pair computes it ONCE, as the
-// tile (rows = the other block, columns = its own block): column sums for its own genes, row sums for the genes of the
-// other block, the similarity transposed into its own rows and directly into the row owner's rows over NVLink.  Half the
-// MMAs and half the power chains of the column-block schedule; the ranks' partial connectivities are summed by the caller.
+// Sharded SYMMETRIC sweep (multi-GPU): the unordered pairs of 128-gene blocks are dealt out over the ranks and the rank
+// that gets a pair computes it ONCE, as the tile (rows = the other block, columns = its own block): column sums for its
+// own genes, row sums for the genes of the other block, the similarity transposed into its own rows -- and in the other
+// orientation to the owner of the rows.  Half the MMAs and half the power chains of the column-block schedule; the
+// ranks' partial connectivities are summed by the caller.  Two ways to reach the row owner:
+//   direct (two ranks): pair {a, b} goes to the owner of a if a + b is even, else to the owner of b; the kernel stores
+//     into the peer's block over NVLink (measured: free with ONE peer, but 4.5x the kernel's time with three);
+//   staged (more ranks): between ranks r < q, r takes the pairs whose q-block lies in the lower half of q's blocks and
+//     q the others, so that what a rank owes a peer is ONE rectangle; the kernel writes it into a local staging
+//     rectangle, the tiles bound for peers run first, and the copy engines push the rectangles (735 GB/s per pair)
+//     while a second launch does the rank's own-own pairs.
 // ---------------------------------------------------------------------------------------------------------------
 namespace {
+struct DistRegion {  // what this rank computes for the rows of peer o: global rows [r0, r1) x global columns [c0, c1)
+  int64_t r0 = 0, r1 = 0, c0 = 0, c1 = 0;
+};
 struct DistPlan {
   int2* d_list = nullptr;
   int *d_cstart = nullptr, *d_row_off = nullptr, *d_row_idx = nullptr;
   std::vector<int2> list;
-  int T = 0;
+  int64_t T[2] = {0, 0};  // part 0: tiles whose rows belong to a peer; part 1: own rows
+  DistRegion region[8];
+  cudaStream_t push_stream = nullptr;
+  cudaEvent_t ev_first = nullptr, ev_pushed = nullptr;
+  bool ready = false;
 };
 std::map<std::vector<int64_t>, DistPlan> g_dist_plans;
 std::mutex g_dist_mu;
 
-// The tiles of one rank, column-major: x = 128-row block, y = 64-column tile of the rank's column block;
-// cstart[jt] .. cstart[jt + 1] = the tiles of column tile jt.
-void dist_tile_list(int64_t n, int world, int rank, int64_t per, std::vector<int2>& list, std::vector<int>& cstart) {
+inline int64_t dist_ncols(int64_t n, int rank, int64_t per) {
   const int64_t col0 = (int64_t)rank * per;
-  const int64_t ncols = col0 >= n ? 0 : (col0 + per <= n ? per : n - col0);
-  const int64_t B = (n + 127) / 128, CT = (ncols + kSweepBN - 1) / kSweepBN;
-  auto owner = [&](int64_t blk) { return (blk * 128) / per; };
-  cstart.assign(CT + 1, 0);
-  list.clear();
-  for (int64_t jt = 0; jt < CT; ++jt) {
-    cstart[jt] = (int)list.size();
-    const int64_t gb = (col0 + jt * kSweepBN) / 128;
-    for (int64_t a = 0; a < B; ++a) {
-      bool mine;
-      if (a == gb) mine = true;
-      else if (owner(a) == rank) mine = a < gb;  // a pair of two own blocks: once, in the upper orientation
-      else {
-        const int64_t lo = a < gb ? a : gb, hi = a < gb ? gb : a;
-        mine = (((lo + hi) & 1) == 0 ? owner(lo) : owner(hi)) == rank;
-      }
-      if (mine) list.push_back(make_int2((int)a, (int)jt));
-    }
+  return col0 >= n ? 0 : (col0 + per <= n ? per : n - col0);
+}
+
+// Does `rank` form the tile (rows = block a, columns inside block gb of its own column block)?
+inline bool dist_mine(int64_t a, int64_t gb, int rank, int64_t per, int64_t n, bool staged) {
+  const int64_t oa = (a * 128) / per;
+  if (a == gb) return true;
+  if (oa == rank) return a < gb;  // a pair of two own blocks: once, in the upper orientation
+  if (!staged) {
+    const int64_t lo = a < gb ? a : gb, hi = a < gb ? gb : a;
+    return (((lo + hi) & 1) == 0 ? (lo * 128) / per : (hi * 128) / per) == rank;
   }
-  cstart[CT] = (int)list.size();
+  // staged: the split runs through the blocks of the HIGHER rank of the two
+  const int hi_rank = oa > rank ? (int)oa : rank;
+  const int64_t b0 = (int64_t)hi_rank * per / 128;
+  const int64_t b1 = b0 + (dist_ncols(n, hi_rank, per) + 127) / 128;
+  const int64_t mid = b0 + (b1 - b0 + 1) / 2;
+  return oa > rank ? (a < mid) : (gb >= mid);
+}
+
+// The tiles of one rank, column-major; x = 128-row block, y = 64-column tile of the rank's column block;
+// cstart[q * (CT + 1) + jt] = start of column tile jt in part q.  Staged mode: part 0 = rows of a peer, part 1 = own
+// rows (two launches); direct mode: everything in part 0.
+void dist_tile_list(int64_t n, int world, int rank, int64_t per, bool staged, std::vector<int2>& list,
+                    std::vector<int>& cstart, int64_t T[2]) {
+  const int64_t col0 = (int64_t)rank * per, ncols = dist_ncols(n, rank, per);
+  const int64_t B = (n + 127) / 128, CT = (ncols + kSweepBN - 1) / kSweepBN;
+  (void)world;
+  cstart.assign(2 * (CT + 1), 0);
+  list.clear();
+  for (int part = 0; part < 2; ++part) {
+    const size_t before = list.size();
+    for (int64_t jt = 0; jt < CT; ++jt) {
+      cstart[part * (CT + 1) + jt] = (int)list.size();
+      const int64_t gb = (col0 + jt * kSweepBN) / 128;
+      for (int64_t a = 0; a < B; ++a) {
+        const bool own_rows = (a * 128) / per == rank;
+        if ((staged && own_rows) != (part == 1)) continue;
+        if (dist_mine(a, gb, rank, per, n, staged)) list.push_back(make_int2((int)a, (int)jt));
+      }
+    }
+    cstart[part * (CT + 1) + CT] = (int)list.size();
+    T[part] = (int64_t)(list.size() - before);
+  }
+}
+
+int dist_max_seg(const std::vector<int2>& list, int64_t tb, int64_t T, int G) {
+  int max_seg = 1;
+  for (int b = 0; b < G; ++b) {
+    int64_t t0, t1;
+    sweep_range(T, G, b, t0, t1);
+    if (t0 >= t1) continue;
+    const int seg = list[tb + t1 - 1].y - list[tb + t0].y + 1;
+    if (seg > max_seg) max_seg = seg;
+  }
+  return max_seg;
+}
+
+bool dist_staged(int world) {
+  static const char* e = getenv("B200WGCNA_SWEEP_PUSH");  // development: "direct" / "staged" for any number of ranks
+  if (e && e[0] == 'd') return false;
+  if (e && e[0] == 's') return true;
+  return world > 2;
 }
 }  // namespace
 
@@ -939,7 +1009,8 @@ extern "C" int64_t b200w_sweep_dist_tiles(int64_t n, int world, int rank, int64_
   if (n < 1 || world < 2 || world > 8 || rank < 0 || rank >= world || per < 256 || per % 256) return -1;
   std::vector<int2> list;
   std::vector<int> cstart;
-  dist_tile_list(n, world, rank, per, list, cstart);
+  int64_t T[2];
+  dist_tile_list(n, world, rank, per, dist_staged(world), list, cstart, T);
   if (out_xy != nullptr && capacity >= (int64_t)list.size())
     for (size_t t = 0; t < list.size(); ++t) {
       out_xy[2 * t] = list[t].x;
@@ -967,24 +1038,53 @@ extern "C" int b200w_dev_sweep_dist(const double* dZ, const uint8_t* d_bad, int6
     prm.istep[q] = (s == 1.0) ? 1 : (s == 2.0 ? 2 : 0);
     if (!prm.istep[q]) return fail(B200W_E_UNSUPPORTED, "sweep_dist: power steps must be 1 or 2");
   }
-  const int64_t col0 = (int64_t)rank * per;
-  const int64_t ncols = col0 >= n ? 0 : (col0 + per <= n ? per : n - col0);
+  for (int r = 0; r < world; ++r)
+    if (!peer_sim[r]) return fail(B200W_E_INVALID, "sweep_dist: peer_sim[%d] is NULL", r);
+  const bool staged = dist_staged(world);
+  const int64_t col0 = (int64_t)rank * per, ncols = dist_ncols(n, rank, per);
   const int64_t B = (n + 127) / 128, CT = (ncols + kSweepBN - 1) / kSweepBN;
   int sms = 0;
   B200W_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   std::lock_guard<std::mutex> lk(g_dist_mu);
-  DistPlan& plan = g_dist_plans[{(int64_t)device, n, (int64_t)world, (int64_t)rank, per}];
-  if (plan.d_cstart == nullptr) {
+  DistPlan& plan = g_dist_plans[{(int64_t)device, n, (int64_t)world, (int64_t)rank, per, (int64_t)staged}];
+  if (!plan.ready) {
     std::vector<int> cstart;
-    dist_tile_list(n, world, rank, per, plan.list, cstart);
-    plan.T = (int)plan.list.size();
+    dist_tile_list(n, world, rank, per, staged, plan.list, cstart, plan.T);
+    const int64_t Tall = plan.T[0] + plan.T[1];
     std::vector<int> row_off(B + 1, 0), row_idx;
-    for (int64_t a = 0; a < B; ++a) {
-      row_off[a] = (int)row_idx.size();
-      for (int t = 0; t < plan.T; ++t)
-        if (plan.list[t].x == a && a != (col0 + (int64_t)plan.list[t].y * kSweepBN) / 128) row_idx.push_back(t);
+    {  // two-pass tiles (off the diagonal block) by row block, in list order
+      std::vector<std::vector<int>> by_row(B);
+      for (int64_t t = 0; t < Tall; ++t) {
+        const int64_t a = plan.list[t].x;
+        if (a != (col0 + (int64_t)plan.list[t].y * kSweepBN) / 128) by_row[a].push_back((int)t);
+      }
+      for (int64_t a = 0; a < B; ++a) {
+        row_off[a] = (int)row_idx.size();
+        row_idx.insert(row_idx.end(), by_row[a].begin(), by_row[a].end());
+      }
+      row_off[B] = (int)row_idx.size();
     }
-    row_off[B] = (int)row_idx.size();
+    for (int o = 0; o < world; ++o) {  // the rectangle owed to peer o (staged mode)
+      DistRegion& rg = plan.region[o];
+      if (o == rank || !staged) continue;
+      const int64_t o_rows = dist_ncols(n, o, per);
+      if (o_rows == 0 || ncols == 0) continue;
+      const int hi_rank = o > rank ? o : rank;
+      const int64_t b0 = (int64_t)hi_rank * per / 128, b1 = b0 + (dist_ncols(n, hi_rank, per) + 127) / 128;
+      const int64_t mid = b0 + (b1 - b0 + 1) / 2;
+      if (o > rank) {  // rows: the lower half of o's blocks; columns: all of mine
+        rg.r0 = (int64_t)o * per;
+        rg.r1 = mid * 128 < n ? mid * 128 : n;
+        rg.c0 = col0;
+        rg.c1 = col0 + ncols;
+      } else {  // rows: all of o's; columns: the upper half of my blocks
+        rg.r0 = (int64_t)o * per;
+        rg.r1 = rg.r0 + o_rows;
+        rg.c0 = mid * 128;
+        rg.c1 = col0 + ncols;
+      }
+      if (rg.r1 <= rg.r0 || rg.c1 <= rg.c0) rg = DistRegion();
+    }
     B200W_CUDA(cudaMalloc(&plan.d_list, (plan.list.size() + 1) * sizeof(int2)));
     B200W_CUDA(cudaMalloc(&plan.d_cstart, cstart.size() * sizeof(int)));
     B200W_CUDA(cudaMalloc(&plan.d_row_off, row_off.size() * sizeof(int)));
@@ -993,43 +1093,88 @@ extern "C" int b200w_dev_sweep_dist(const double* dZ, const uint8_t* d_bad, int6
     B200W_CUDA(cudaMemcpy(plan.d_cstart, cstart.data(), cstart.size() * sizeof(int), cudaMemcpyHostToDevice));
     B200W_CUDA(cudaMemcpy(plan.d_row_off, row_off.data(), row_off.size() * sizeof(int), cudaMemcpyHostToDevice));
     B200W_CUDA(cudaMemcpy(plan.d_row_idx, row_idx.data(), row_idx.size() * sizeof(int), cudaMemcpyHostToDevice));
-  }
-  const int64_t T = plan.T;
-  Scratch part, rowpart;
-  int G = 1, max_seg = 1;
-  if (T > 0) {
-    G = (int)(T < sms ? T : sms);
-    for (int b = 0; b < G; ++b) {
-      int64_t t0, t1;
-      sweep_range(T, G, b, t0, t1);
-      if (t0 >= t1) continue;
-      const int seg = plan.list[t1 - 1].y - plan.list[t0].y + 1;
-      if (seg > max_seg) max_seg = seg;
+    if (staged) {
+      B200W_CUDA(cudaStreamCreateWithFlags(&plan.push_stream, cudaStreamNonBlocking));
+      B200W_CUDA(cudaEventCreateWithFlags(&plan.ev_first, cudaEventDisableTiming));
+      B200W_CUDA(cudaEventCreateWithFlags(&plan.ev_pushed, cudaEventDisableTiming));
     }
-    prm.Z = dZ; prm.bad = d_bad; prm.n = n; prm.ldk = b200w_padded_k(m); prm.col0 = col0; prm.ncols = ncols;
-    prm.RT = B; prm.T = T; prm.P = P; prm.net_type = net_type; prm.simple_steps = 1; prm.max_seg = max_seg;
-    prm.symmetric = 0; prm.sim_transposed = 1; prm.dist = 1; prm.per_rows = per; prm.tile_list = plan.d_list;
-    prm.adj_power = 1.0; prm.adj_ipower = 1;
-    for (int r = 0; r < 8; ++r) prm.peer_sim[r] = r < world ? (double*)peer_sim[r] : nullptr;
-    prm.sim = (double*)peer_sim[rank];
-    if (!prm.sim) return fail(B200W_E_INVALID, "sweep_dist: peer_sim[rank] is NULL");
-    B200W_CUDA(part.alloc((size_t)G * max_seg * P * kSweepBN * sizeof(double), st));
-    B200W_CUDA(rowpart.alloc((size_t)T * P * 128 * sizeof(double), st));
-    prm.partial = part.as<double>();
-    prm.rowpart = rowpart.as<double>();
-    if (int e = sweep_i8_launch(prm, m, CT, P, G, device, st)) return e;
-  } else {
-    B200W_CUDA(part.alloc(16, st));
-    B200W_CUDA(rowpart.alloc(16, st));
+    plan.ready = true;
   }
-  if (T > 0) {
-    dim3 rgrid((unsigned)B, (unsigned)P);
-    sweep_reduce_dist_kernel<<<rgrid, 128, 0, st>>>(part.as<double>(), rowpart.as<double>(), plan.d_list, plan.d_cstart,
-                                                    plan.d_row_off, plan.d_row_idx, G, max_seg, P, T, n, col0, ncols,
-                                                    d_kpart);
-    B200W_LAUNCHED();
-  } else {
+  const int64_t Tall = plan.T[0] + plan.T[1];
+  if (Tall == 0) {
     B200W_CUDA(cudaMemsetAsync(d_kpart, 0, (size_t)P * n * sizeof(double), st));
+    return 0;
   }
+  // direct mode: one launch over the whole list; staged: peers' tiles first, own tiles in a second launch
+  DistReduceParts parts = {};
+  parts.nparts = 2;
+  int64_t tb[2] = {0, plan.T[0]}, Tq[2] = {plan.T[0], plan.T[1]};
+  Scratch part[2], rowpart, stage;
+  for (int q = 0; q < 2; ++q) {
+    const int G = (int)(Tq[q] < sms ? (Tq[q] > 0 ? Tq[q] : 1) : sms);
+    const int max_seg = Tq[q] > 0 ? dist_max_seg(plan.list, tb[q], Tq[q], G) : 1;
+    B200W_CUDA(part[q].alloc((size_t)G * max_seg * P * kSweepBN * sizeof(double), st));
+    parts.partial[q] = part[q].as<double>();
+    parts.tb[q] = tb[q];
+    parts.T[q] = Tq[q];
+    parts.G[q] = G;
+    parts.max_seg[q] = max_seg;
+  }
+  B200W_CUDA(rowpart.alloc((size_t)Tall * P * 128 * sizeof(double), st));
+  prm.Z = dZ; prm.bad = d_bad; prm.n = n; prm.ldk = b200w_padded_k(m); prm.col0 = col0; prm.ncols = ncols;
+  prm.RT = B; prm.P = P; prm.net_type = net_type; prm.simple_steps = 1;
+  prm.symmetric = 0; prm.sim_transposed = 1; prm.dist = 1; prm.per_rows = per; prm.tile_list = plan.d_list;
+  prm.adj_power = 1.0; prm.adj_ipower = 1;
+  prm.sim = (double*)peer_sim[rank];
+  prm.rowpart = rowpart.as<double>();
+  size_t stage_elems = 0;
+  size_t stage_off[8] = {0};
+  for (int o = 0; o < world; ++o) {
+    const DistRegion& rg = plan.region[o];
+    stage_off[o] = stage_elems;
+    if (staged && o != rank) stage_elems += (size_t)(rg.r1 - rg.r0) * (size_t)(rg.c1 - rg.c0);
+  }
+  if (staged) B200W_CUDA(stage.alloc(stage_elems * sizeof(double), st));
+  for (int o = 0; o < world; ++o) {
+    const DistRegion& rg = plan.region[o];
+    if (staged && o != rank) {
+      prm.peer_sim[o] = stage.as<double>() + stage_off[o];
+      prm.peer_pitch[o] = rg.c1 - rg.c0;
+      prm.peer_row0[o] = rg.r0;
+      prm.peer_col0[o] = rg.c0;
+    } else {
+      prm.peer_sim[o] = (double*)peer_sim[o];
+      prm.peer_pitch[o] = n;
+      prm.peer_row0[o] = (int64_t)o * per;
+      prm.peer_col0[o] = 0;
+    }
+  }
+  prm.t_begin = 0;
+  prm.T = Tq[0];
+  prm.max_seg = parts.max_seg[0];
+  prm.partial = part[0].as<double>();
+  SweepSecond second = {tb[1], Tq[1], parts.G[1], parts.max_seg[1], part[1].as<double>(),
+                        staged ? plan.ev_first : nullptr};
+  if (int e = sweep_i8_launch(prm, m, CT, P, parts.G[0], device, st, &second)) return e;
+  if (staged) {
+    // the rectangles are complete when the first launch is: the copy engines push them into the peers' blocks while
+    // the second launch runs
+    B200W_CUDA(cudaStreamWaitEvent(plan.push_stream, plan.ev_first, 0));
+    for (int d = 1; d < world; ++d) {
+      const int o = (rank + d) % world;
+      const DistRegion& rg = plan.region[o];
+      if (rg.r1 <= rg.r0) continue;
+      double* dst = (double*)peer_sim[o] + (rg.r0 - (int64_t)o * per) * n + rg.c0;
+      B200W_CUDA(cudaMemcpy2DAsync(dst, (size_t)n * sizeof(double), prm.peer_sim[o],
+                                   (size_t)(rg.c1 - rg.c0) * sizeof(double), (size_t)(rg.c1 - rg.c0) * sizeof(double),
+                                   (size_t)(rg.r1 - rg.r0), cudaMemcpyDeviceToDevice, plan.push_stream));
+    }
+    B200W_CUDA(cudaEventRecord(plan.ev_pushed, plan.push_stream));
+  }
+  dim3 rgrid((unsigned)B, (unsigned)P);
+  sweep_reduce_dist_kernel<<<rgrid, 128, 0, st>>>(parts, rowpart.as<double>(), plan.d_list, plan.d_cstart,
+                                                  plan.d_row_off, plan.d_row_idx, P, n, col0, ncols, (int)CT, d_kpart);
+  B200W_LAUNCHED();
+  if (staged) B200W_CUDA(cudaStreamWaitEvent(st, plan.ev_pushed, 0));  // (also before the staging area is freed)
   return 0;
 }

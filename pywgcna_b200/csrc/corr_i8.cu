@@ -218,10 +218,11 @@ struct TileWalk {
   __device__ __forceinline__ void init(const SweepParams& prm) {
     int64_t t0;
     sweep_range(prm.T, gridDim.x, blockIdx.x, t0, t1);
+    list = prm.tile_list;
+    if (list != nullptr) { t0 += prm.t_begin; t1 += prm.t_begin; }
     t = t0;
     sym = prm.symmetric != 0;
     RT = prm.RT;
-    list = prm.tile_list;
     if (t0 >= t1) return;
     if (list != nullptr) {
       const int2 e = list[t0];
@@ -479,11 +480,13 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
       const bool write_direct = prm.sim != nullptr && (prm.dist ? two_pass : !prm.sim_transposed) && col_in;
       const bool keep_out = prm.sim != nullptr && prm.sim_transposed;
       double* out_ptr = prm.sim != nullptr ? prm.sim + row_base * n + gj : nullptr;
+      int64_t out_pitch = n;
       if (prm.dist && prm.sim != nullptr) {
         // the tile's 128 rows belong to one rank (row blocks start on 256-row boundaries): element (gi, gj) goes into
-        // that rank's block -- its own HBM or a peer's over NVLink
+        // that rank's block -- its own HBM, a peer's over NVLink, or a local rectangle staged for the copy engines
         const int64_t owner = i0 / prm.per_rows;
-        out_ptr = prm.peer_sim[owner] + (row_base - owner * prm.per_rows) * n + gj;
+        out_pitch = prm.peer_pitch[owner];
+        out_ptr = prm.peer_sim[owner] + (row_base - prm.peer_row0[owner]) * out_pitch + (gj - prm.peer_col0[owner]);
       }
       const int net_type = prm.net_type;
 
@@ -540,7 +543,7 @@ sweep_i8_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant
           if (prm.sim != nullptr) {
             const double s_out = nan_pair ? qnan : out_value(sv);
             if (keep_out) my[r * kWarpPitch + lane] = s_out;  // stored by the transposed pass below
-            if (write_direct && valid) out_ptr[(int64_t)r * n] = s_out;
+            if (write_direct && valid) out_ptr[(int64_t)r * out_pitch] = s_out;
           }
           // chain start: the diagonal counts as 1 even for a NaN gene (wgcna.py:897), NaN pairs are skipped by
           // nansum (:915), rows past the matrix contribute nothing
@@ -685,7 +688,8 @@ bool corr_i8_enabled(int64_t m, int64_t n) {
 
 // One launch of the tcgen05 sweep / adjacency engine.  prm is filled by the caller as for corr.cu's sweep_kernel
 // (partial / rowpart / T / max_seg / symmetric ...); planes and scales are made here, stream ordered.
-int sweep_i8_launch(SweepParams prm, int64_t m, int64_t CT, int P, int G, int device, cudaStream_t st) {
+int sweep_i8_launch(SweepParams prm, int64_t m, int64_t CT, int P, int G, int device, cudaStream_t st,
+                    const SweepSecond* second) {
   EncodeTiledFn encode = corr_encode_tiled();
   if (!encode) return fail(B200W_E_CUDA, "corr_i8: cuTensorMapEncodeTiled not available from the driver");
   const int64_t n = prm.n;
@@ -726,8 +730,22 @@ int sweep_i8_launch(SweepParams prm, int64_t m, int64_t CT, int P, int G, int de
   // are not stored
   auto launch = [&](auto kern) -> int {
     B200W_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCorrSmem));
-    kern<<<G, kCThreads, kCorrSmem, st>>>(tmapA, tmapB, prm, (int)(ldkb / kCKB));
-    B200W_LAUNCHED();
+    if (prm.T > 0) {
+      kern<<<G, kCThreads, kCorrSmem, st>>>(tmapA, tmapB, prm, (int)(ldkb / kCKB));
+      B200W_LAUNCHED();
+    }
+    if (second != nullptr) {  // another range of the tile list on the same planes
+      if (second->after_first) B200W_CUDA(cudaEventRecord(second->after_first, st));
+      SweepParams p2 = prm;
+      p2.t_begin = second->t_begin;
+      p2.T = second->T;
+      p2.max_seg = second->max_seg;
+      p2.partial = second->partial;
+      if (p2.T > 0) {
+        kern<<<second->G, kCThreads, kCorrSmem, st>>>(tmapA, tmapB, p2, (int)(ldkb / kCKB));
+        B200W_LAUNCHED();
+      }
+    }
     return 0;
   };
   bool all_one = true;

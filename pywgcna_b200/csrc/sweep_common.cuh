@@ -38,9 +38,22 @@ struct SweepParams {
   // and its similarity goes to BOTH owners: transposed into the rank's own rows, directly into the row owner's block
   // (peer_sim[owner], peer-mapped HBM) from inside the kernel
   const int2* tile_list;
-  double* peer_sim[8];
+  int64_t t_begin;       // this launch walks tile_list[t_begin, t_begin + T)
+  double* peer_sim[8];   // where the tile's direct orientation goes, by owner of its rows: the owner's block itself
+  int64_t peer_pitch[8]; // (own HBM / a peer's over NVLink: pitch n, row0 = owner * per_rows, col0 = 0) or a local staging
+  int64_t peer_row0[8];  // rectangle that the copy engines push to the owner afterwards:
+  int64_t peer_col0[8];  //   element (gi, gj) -> peer_sim[o][(gi - peer_row0[o]) * peer_pitch[o] + gj - peer_col0[o]]
   int64_t per_rows;
   int dist;
+};
+
+// second launch of one sweep_i8_launch call over another range of the tile list (same planes): own partial slots,
+// an event recorded between the two launches
+struct SweepSecond {
+  int64_t t_begin, T;
+  int G, max_seg;
+  double* partial;
+  cudaEvent_t after_first;
 };
 
 __host__ __device__ __forceinline__ void sweep_range(int64_t T, int64_t G, int64_t b, int64_t& t0, int64_t& t1) {
@@ -88,7 +101,8 @@ __device__ __forceinline__ void int_pow4(double (&s)[4], int e) {
 #endif
 
 // corr_i8.cu
-int sweep_i8_launch(SweepParams prm, int64_t m, int64_t CT, int P, int G, int device, cudaStream_t st);
+int sweep_i8_launch(SweepParams prm, int64_t m, int64_t CT, int P, int G, int device, cudaStream_t st,
+                    const SweepSecond* second = nullptr);
 bool corr_i8_enabled(int64_t m, int64_t n);
 
 }  // namespace b200w

@@ -162,14 +162,12 @@ class DeviceNetwork:
             keep_similarity = os.environ.get("B200WGCNA_KEEP_SIMILARITY", "1") != "0"
         self.keep_similarity = bool(keep_similarity)
         # sweep of the sharded run: "symmetric" = block pairs dealt out over the ranks, every correlation tile formed
-        # once and its similarity stored into both owners' blocks from inside the kernel (b200w_dev_sweep_dist);
-        # "full" = every rank sweeps its whole column block.  Measured at C3 (tools/sweepdist_probe.py,
-        # profiles/r02_sweepdist_probe_n4*.json): with ONE peer the plain stores over NVLink are free (2 GPUs: sweep
-        # 32.9 -> 21.1 ms; 4 GPUs with only rank + 1 mapped: 11.6 ms = the kernel with every store kept local), with
-        # two peers the kernel takes 28.7 ms and with three 52 ms against 16.7 ms for "full"; visiting the peers one
-        # after the other (tile list ordered by destination) made it worse (67-79 ms).  Until that is understood the
-        # default is symmetric for two ranks only.
-        default_mode = "symmetric" if self.world == 2 else "full"
+        # once and its similarity delivered to both owners' blocks (b200w_dev_sweep_dist: with one peer stored over
+        # NVLink from inside the kernel; with more, staged in a local rectangle per peer that the copy engines push
+        # while the kernel does the rank's own pairs -- plain stores to three peers made the kernel 4.5x slower,
+        # profiles/r02_sweepdist_probe_n4*.json); "full" = every rank sweeps its whole column block.
+        # C3: 2 GPUs 32.9 -> 21.1 ms, 4 GPUs 16.7 -> 12.7 ms.
+        default_mode = "symmetric"
         self.sym_sweep = (self.world > 1 and bool(self.use_dist) and self.keep_similarity
                           and os.environ.get("B200WGCNA_SWEEP_DIST", default_mode) == "symmetric")
         self._sync_token = None
