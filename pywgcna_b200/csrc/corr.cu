@@ -430,13 +430,14 @@ __global__ void sweep_reduce_sym_kernel(const double* __restrict__ partial, cons
 //   own genes:   the column slots of their column tile (CTAs in list order) - 1        (wgcna.py:915)
 //   every gene:  + the row slots of the listed tiles whose row block holds it (CSR row_off / row_idx)
 // -- the caller sums the partial vectors of the ranks (all-reduce).  Fixed order, no atomics.
-// Sharded symmetric sweep: this rank's partial connectivities of all genes.  The tile list comes in up to two parts
+// Sharded symmetric sweep: this rank's partial connectivities of all genes.  The tile list comes in up to eight parts
 // (launches): part q walks list[tb[q], tb[q] + Tq[q]) with Gq[q] CTAs, its column tile jt's run of the list is
 // cstart[q * (CT + 1) + jt ..]; row sums by the CSR (row_off, row_idx) over list positions.
+constexpr int kDistMaxParts = 8;
 struct DistReduceParts {
-  const double* partial[2];
-  int64_t tb[2], T[2];
-  int G[2], max_seg[2];
+  const double* partial[kDistMaxParts];
+  int64_t tb[kDistMaxParts], T[kDistMaxParts];
+  int G[kDistMaxParts], max_seg[kDistMaxParts];
   int nparts;
 };
 __global__ void __launch_bounds__(128)
@@ -925,10 +926,11 @@ struct DistPlan {
   int2* d_list = nullptr;
   int *d_cstart = nullptr, *d_row_off = nullptr, *d_row_idx = nullptr;
   std::vector<int2> list;
-  int64_t T[2] = {0, 0};  // part 0: tiles whose rows belong to a peer; part 1: own rows
+  int nparts = 1;
+  int64_t T[kDistMaxParts] = {0};  // staged: part d - 1 = rows of rank + d (d = 1 .. world - 1), last part = own rows
   DistRegion region[8];
   cudaStream_t push_stream = nullptr;
-  cudaEvent_t ev_first = nullptr, ev_pushed = nullptr;
+  cudaEvent_t ev_part[kDistMaxParts] = {nullptr}, ev_pushed = nullptr;  // ev_part[q]: part q has been computed
   bool ready = false;
 };
 std::map<std::vector<int64_t>, DistPlan> g_dist_plans;
@@ -956,30 +958,32 @@ inline bool dist_mine(int64_t a, int64_t gb, int rank, int64_t per, int64_t n, b
   return oa > rank ? (a < mid) : (gb >= mid);
 }
 
-// The tiles of one rank, column-major; x = 128-row block, y = 64-column tile of the rank's column block;
-// cstart[q * (CT + 1) + jt] = start of column tile jt in part q.  Staged mode: part 0 = rows of a peer, part 1 = own
-// rows (two launches); direct mode: everything in part 0.
-void dist_tile_list(int64_t n, int world, int rank, int64_t per, bool staged, std::vector<int2>& list,
-                    std::vector<int>& cstart, int64_t T[2]) {
+// The tiles of one rank; x = 128-row block, y = 64-column tile of the rank's column block; column-major inside a part,
+// cstart[q * (CT + 1) + jt] = start of column tile jt in part q.  Staged mode: one part (launch) per peer in the order
+// rank + 1, rank + 2, ... -- its rectangle is pushed while the next part runs -- and the own rows last; direct mode:
+// everything in part 0.  Returns the number of parts.
+int dist_tile_list(int64_t n, int world, int rank, int64_t per, bool staged, std::vector<int2>& list,
+                   std::vector<int>& cstart, int64_t* T) {
   const int64_t col0 = (int64_t)rank * per, ncols = dist_ncols(n, rank, per);
   const int64_t B = (n + 127) / 128, CT = (ncols + kSweepBN - 1) / kSweepBN;
-  (void)world;
-  cstart.assign(2 * (CT + 1), 0);
+  const int nparts = staged ? world : 1;
+  cstart.assign((size_t)nparts * (CT + 1), 0);
   list.clear();
-  for (int part = 0; part < 2; ++part) {
+  for (int part = 0; part < nparts; ++part) {
+    const int64_t target = staged ? (rank + part + 1) % world : -1;  // (the last part: rank itself)
     const size_t before = list.size();
     for (int64_t jt = 0; jt < CT; ++jt) {
       cstart[part * (CT + 1) + jt] = (int)list.size();
       const int64_t gb = (col0 + jt * kSweepBN) / 128;
       for (int64_t a = 0; a < B; ++a) {
-        const bool own_rows = (a * 128) / per == rank;
-        if ((staged && own_rows) != (part == 1)) continue;
+        if (staged && (a * 128) / per != target) continue;
         if (dist_mine(a, gb, rank, per, n, staged)) list.push_back(make_int2((int)a, (int)jt));
       }
     }
     cstart[part * (CT + 1) + CT] = (int)list.size();
     T[part] = (int64_t)(list.size() - before);
   }
+  return nparts;
 }
 
 int dist_max_seg(const std::vector<int2>& list, int64_t tb, int64_t T, int G) {
@@ -1009,7 +1013,7 @@ extern "C" int64_t b200w_sweep_dist_tiles(int64_t n, int world, int rank, int64_
   if (n < 1 || world < 2 || world > 8 || rank < 0 || rank >= world || per < 256 || per % 256) return -1;
   std::vector<int2> list;
   std::vector<int> cstart;
-  int64_t T[2];
+  int64_t T[kDistMaxParts];
   dist_tile_list(n, world, rank, per, dist_staged(world), list, cstart, T);
   if (out_xy != nullptr && capacity >= (int64_t)list.size())
     for (size_t t = 0; t < list.size(); ++t) {
@@ -1049,8 +1053,8 @@ extern "C" int b200w_dev_sweep_dist(const double* dZ, const uint8_t* d_bad, int6
   DistPlan& plan = g_dist_plans[{(int64_t)device, n, (int64_t)world, (int64_t)rank, per, (int64_t)staged}];
   if (!plan.ready) {
     std::vector<int> cstart;
-    dist_tile_list(n, world, rank, per, staged, plan.list, cstart, plan.T);
-    const int64_t Tall = plan.T[0] + plan.T[1];
+    plan.nparts = dist_tile_list(n, world, rank, per, staged, plan.list, cstart, plan.T);
+    const int64_t Tall = (int64_t)plan.list.size();
     std::vector<int> row_off(B + 1, 0), row_idx;
     {  // two-pass tiles (off the diagonal block) by row block, in list order
       std::vector<std::vector<int>> by_row(B);
@@ -1095,30 +1099,34 @@ extern "C" int b200w_dev_sweep_dist(const double* dZ, const uint8_t* d_bad, int6
     B200W_CUDA(cudaMemcpy(plan.d_row_idx, row_idx.data(), row_idx.size() * sizeof(int), cudaMemcpyHostToDevice));
     if (staged) {
       B200W_CUDA(cudaStreamCreateWithFlags(&plan.push_stream, cudaStreamNonBlocking));
-      B200W_CUDA(cudaEventCreateWithFlags(&plan.ev_first, cudaEventDisableTiming));
+      for (int q = 0; q < plan.nparts; ++q)
+        B200W_CUDA(cudaEventCreateWithFlags(&plan.ev_part[q], cudaEventDisableTiming));
       B200W_CUDA(cudaEventCreateWithFlags(&plan.ev_pushed, cudaEventDisableTiming));
     }
     plan.ready = true;
   }
-  const int64_t Tall = plan.T[0] + plan.T[1];
+  const int64_t Tall = (int64_t)plan.list.size();
   if (Tall == 0) {
     B200W_CUDA(cudaMemsetAsync(d_kpart, 0, (size_t)P * n * sizeof(double), st));
     return 0;
   }
-  // direct mode: one launch over the whole list; staged: peers' tiles first, own tiles in a second launch
+  // direct mode: one launch over the whole list; staged: one launch per peer, then the own rows
+  const int nparts = plan.nparts;
   DistReduceParts parts = {};
-  parts.nparts = 2;
-  int64_t tb[2] = {0, plan.T[0]}, Tq[2] = {plan.T[0], plan.T[1]};
-  Scratch part[2], rowpart, stage;
-  for (int q = 0; q < 2; ++q) {
-    const int G = (int)(Tq[q] < sms ? (Tq[q] > 0 ? Tq[q] : 1) : sms);
-    const int max_seg = Tq[q] > 0 ? dist_max_seg(plan.list, tb[q], Tq[q], G) : 1;
+  parts.nparts = nparts;
+  Scratch part[kDistMaxParts], rowpart, stage;
+  int64_t tb = 0;
+  for (int q = 0; q < nparts; ++q) {
+    const int64_t Tq = plan.T[q];
+    const int G = (int)(Tq < sms ? (Tq > 0 ? Tq : 1) : sms);
+    const int max_seg = Tq > 0 ? dist_max_seg(plan.list, tb, Tq, G) : 1;
     B200W_CUDA(part[q].alloc((size_t)G * max_seg * P * kSweepBN * sizeof(double), st));
     parts.partial[q] = part[q].as<double>();
-    parts.tb[q] = tb[q];
-    parts.T[q] = Tq[q];
+    parts.tb[q] = tb;
+    parts.T[q] = Tq;
     parts.G[q] = G;
     parts.max_seg[q] = max_seg;
+    tb += Tq;
   }
   B200W_CUDA(rowpart.alloc((size_t)Tall * P * 128 * sizeof(double), st));
   prm.Z = dZ; prm.bad = d_bad; prm.n = n; prm.ldk = b200w_padded_k(m); prm.col0 = col0; prm.ncols = ncols;
@@ -1150,20 +1158,22 @@ extern "C" int b200w_dev_sweep_dist(const double* dZ, const uint8_t* d_bad, int6
     }
   }
   prm.t_begin = 0;
-  prm.T = Tq[0];
+  prm.T = parts.T[0];
   prm.max_seg = parts.max_seg[0];
   prm.partial = part[0].as<double>();
-  SweepSecond second = {tb[1], Tq[1], parts.G[1], parts.max_seg[1], part[1].as<double>(),
-                        staged ? plan.ev_first : nullptr};
-  if (int e = sweep_i8_launch(prm, m, CT, P, parts.G[0], device, st, &second)) return e;
+  SweepRange more[kDistMaxParts];
+  for (int q = 1; q < nparts; ++q)
+    more[q - 1] = {parts.tb[q], parts.T[q], parts.G[q], parts.max_seg[q], part[q].as<double>(),
+                   staged ? plan.ev_part[q - 1] : nullptr};
+  if (int e = sweep_i8_launch(prm, m, CT, P, parts.G[0], device, st, more, nparts - 1)) return e;
   if (staged) {
-    // the rectangles are complete when the first launch is: the copy engines push them into the peers' blocks while
-    // the second launch runs
-    B200W_CUDA(cudaStreamWaitEvent(plan.push_stream, plan.ev_first, 0));
+    // a peer's rectangle is complete when its part is: the copy engines push it into the peer's block while the
+    // following parts run (the last push during the own rows)
     for (int d = 1; d < world; ++d) {
       const int o = (rank + d) % world;
       const DistRegion& rg = plan.region[o];
       if (rg.r1 <= rg.r0) continue;
+      B200W_CUDA(cudaStreamWaitEvent(plan.push_stream, plan.ev_part[d - 1], 0));
       double* dst = (double*)peer_sim[o] + (rg.r0 - (int64_t)o * per) * n + rg.c0;
       B200W_CUDA(cudaMemcpy2DAsync(dst, (size_t)n * sizeof(double), prm.peer_sim[o],
                                    (size_t)(rg.c1 - rg.c0) * sizeof(double), (size_t)(rg.c1 - rg.c0) * sizeof(double),

@@ -689,7 +689,7 @@ bool corr_i8_enabled(int64_t m, int64_t n) {
 // One launch of the tcgen05 sweep / adjacency engine.  prm is filled by the caller as for corr.cu's sweep_kernel
 // (partial / rowpart / T / max_seg / symmetric ...); planes and scales are made here, stream ordered.
 int sweep_i8_launch(SweepParams prm, int64_t m, int64_t CT, int P, int G, int device, cudaStream_t st,
-                    const SweepSecond* second) {
+                    const SweepRange* more, int n_more) {
   EncodeTiledFn encode = corr_encode_tiled();
   if (!encode) return fail(B200W_E_CUDA, "corr_i8: cuTensorMapEncodeTiled not available from the driver");
   const int64_t n = prm.n;
@@ -734,15 +734,16 @@ int sweep_i8_launch(SweepParams prm, int64_t m, int64_t CT, int P, int G, int de
       kern<<<G, kCThreads, kCorrSmem, st>>>(tmapA, tmapB, prm, (int)(ldkb / kCKB));
       B200W_LAUNCHED();
     }
-    if (second != nullptr) {  // another range of the tile list on the same planes
-      if (second->after_first) B200W_CUDA(cudaEventRecord(second->after_first, st));
+    for (int i = 0; i < n_more; ++i) {  // further ranges of the tile list on the same planes
+      const SweepRange& r = more[i];
+      if (r.before) B200W_CUDA(cudaEventRecord(r.before, st));
       SweepParams p2 = prm;
-      p2.t_begin = second->t_begin;
-      p2.T = second->T;
-      p2.max_seg = second->max_seg;
-      p2.partial = second->partial;
+      p2.t_begin = r.t_begin;
+      p2.T = r.T;
+      p2.max_seg = r.max_seg;
+      p2.partial = r.partial;
       if (p2.T > 0) {
-        kern<<<second->G, kCThreads, kCorrSmem, st>>>(tmapA, tmapB, p2, (int)(ldkb / kCKB));
+        kern<<<r.G, kCThreads, kCorrSmem, st>>>(tmapA, tmapB, p2, (int)(ldkb / kCKB));
         B200W_LAUNCHED();
       }
     }

@@ -47,13 +47,13 @@ struct SweepParams {
   int dist;
 };
 
-// second launch of one sweep_i8_launch call over another range of the tile list (same planes): own partial slots,
-// an event recorded between the two launches
-struct SweepSecond {
+// further launches of one sweep_i8_launch call over other ranges of the tile list (same planes): own partial slots,
+// an event recorded BEFORE each of them (= after the launch that precedes it)
+struct SweepRange {
   int64_t t_begin, T;
   int G, max_seg;
   double* partial;
-  cudaEvent_t after_first;
+  cudaEvent_t before;
 };
 
 __host__ __device__ __forceinline__ void sweep_range(int64_t T, int64_t G, int64_t b, int64_t& t0, int64_t& t1) {
@@ -102,7 +102,7 @@ __device__ __forceinline__ void int_pow4(double (&s)[4], int e) {
 
 // corr_i8.cu
 int sweep_i8_launch(SweepParams prm, int64_t m, int64_t CT, int P, int G, int device, cudaStream_t st,
-                    const SweepSecond* second = nullptr);
+                    const SweepRange* more = nullptr, int n_more = 0);
 bool corr_i8_enabled(int64_t m, int64_t n);
 
 }  // namespace b200w
