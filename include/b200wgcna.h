@@ -233,6 +233,11 @@ int b200w_dev_sweep_dist(const double* dZ, const uint8_t* d_bad, int64_t m, int6
  * rank's column block) pairs, in launch order.  Returns the number of tiles (-1: bad arguments) and writes them to
  * out_xy[2 * count] when capacity suffices.  For tests of the schedule: over the ranks every pair of blocks exactly once. */
 int64_t b200w_sweep_dist_tiles(int64_t n, int world, int rank, int64_t per, int32_t* out_xy, int64_t capacity);
+/* Host only: with more than two ranks the half of the similarity that a rank computes for a peer is ONE rectangle, written
+ * to a local staging area by the kernel and pushed into the peer's block by the copy engines.  out[4 * o ..] = {row0, row1,
+ * col0, col1} (global gene indices, half open) of the rectangle `rank` owes peer o, zeros where there is none.  Returns 1
+ * (staged), 0 (two ranks: the kernel stores into the peer directly) or -1 (bad arguments). */
+int b200w_sweep_dist_regions(int64_t n, int world, int rank, int64_t per, int64_t* out /* 4 * world */);
 /* statistics of k[P, ldk >= n] as described at b200w_soft_threshold_stats; d_stats P x (4 + 2 nb),
  * d_buckets P x b200w_sft_exp_buckets() x 2 */
 int b200w_dev_sft_stats(const double* d_k, int P, int64_t n, int64_t ldk, int nbreaks, double* d_stats,

@@ -70,6 +70,7 @@ SIGNATURES = {
     "b200w_dev_sweep_similarity": (_int, [_dp, _dp, _i64, _i64, _dp, _int, _int, _i64, _i64, _dp, _dp, _int, _dp]),
     "b200w_dev_sweep_dist": (_int, [_dp, _dp, _i64, _i64, _dp, _int, _int, _int, _int, _i64, C.POINTER(C.c_void_p), _dp, _int, _dp]),
     "b200w_sweep_dist_tiles": (_i64, [_i64, _int, _int, _i64, _dp, _i64]),
+    "b200w_sweep_dist_regions": (_int, [_i64, _int, _int, _i64, _dp]),
     "b200w_dev_adjacency_from_similarity": (_int, [_dp, _i64, _i64, _dbl, _int, _dp]),
     "b200w_dev_adjacency_from_similarity_dp": (_int, [_dp, _i64, _i64, _dp, _int, _dp]),
     "b200w_dev_adjacency_dp": (_int, [_dp, _dp, _i64, _i64, _int, _dp, _i64, _i64, _dp, _int, _dp]),

@@ -986,6 +986,32 @@ int dist_tile_list(int64_t n, int world, int rank, int64_t per, bool staged, std
   return nparts;
 }
 
+// The rectangle that `rank` owes peer o in staged mode (empty in direct mode, for o == rank and for ranks without genes)
+DistRegion dist_region(int64_t n, int world, int rank, int64_t per, int o, bool staged) {
+  DistRegion rg;
+  (void)world;
+  const int64_t col0 = (int64_t)rank * per, ncols = dist_ncols(n, rank, per);
+  if (o == rank || !staged) return rg;
+  const int64_t o_rows = dist_ncols(n, o, per);
+  if (o_rows == 0 || ncols == 0) return rg;
+  const int hi_rank = o > rank ? o : rank;
+  const int64_t b0 = (int64_t)hi_rank * per / 128, b1 = b0 + (dist_ncols(n, hi_rank, per) + 127) / 128;
+  const int64_t mid = b0 + (b1 - b0 + 1) / 2;
+  if (o > rank) {  // rows: the lower half of o's blocks; columns: all of mine
+    rg.r0 = (int64_t)o * per;
+    rg.r1 = mid * 128 < n ? mid * 128 : n;
+    rg.c0 = col0;
+    rg.c1 = col0 + ncols;
+  } else {  // rows: all of o's; columns: the upper half of my blocks
+    rg.r0 = (int64_t)o * per;
+    rg.r1 = rg.r0 + o_rows;
+    rg.c0 = mid * 128;
+    rg.c1 = col0 + ncols;
+  }
+  if (rg.r1 <= rg.r0 || rg.c1 <= rg.c0) rg = DistRegion();
+  return rg;
+}
+
 int dist_max_seg(const std::vector<int2>& list, int64_t tb, int64_t T, int G) {
   int max_seg = 1;
   for (int b = 0; b < G; ++b) {
@@ -1021,6 +1047,19 @@ extern "C" int64_t b200w_sweep_dist_tiles(int64_t n, int world, int rank, int64_
       out_xy[2 * t + 1] = list[t].y;
     }
   return (int64_t)list.size();
+}
+
+// Host only: the rectangles of the staged mode -- out[4 * o .. ] = {row0, row1, col0, col1} (global gene indices) of what
+// `rank` computes for peer o and the copy engines push into o's block; all zero where there is none.  Returns 1 in staged
+// mode, 0 in direct mode (the kernel stores into the peers itself), -1 for bad arguments.
+extern "C" int b200w_sweep_dist_regions(int64_t n, int world, int rank, int64_t per, int64_t* out) {
+  if (n < 1 || world < 2 || world > 8 || rank < 0 || rank >= world || per < 256 || per % 256 || !out) return -1;
+  const bool staged = dist_staged(world);
+  for (int o = 0; o < world; ++o) {
+    const DistRegion rg = dist_region(n, world, rank, per, o, staged);
+    out[4 * o] = rg.r0; out[4 * o + 1] = rg.r1; out[4 * o + 2] = rg.c0; out[4 * o + 3] = rg.c1;
+  }
+  return staged ? 1 : 0;
 }
 
 extern "C" int b200w_dev_sweep_dist(const double* dZ, const uint8_t* d_bad, int64_t m, int64_t n, const double* h_steps,
@@ -1068,27 +1107,7 @@ extern "C" int b200w_dev_sweep_dist(const double* dZ, const uint8_t* d_bad, int6
       }
       row_off[B] = (int)row_idx.size();
     }
-    for (int o = 0; o < world; ++o) {  // the rectangle owed to peer o (staged mode)
-      DistRegion& rg = plan.region[o];
-      if (o == rank || !staged) continue;
-      const int64_t o_rows = dist_ncols(n, o, per);
-      if (o_rows == 0 || ncols == 0) continue;
-      const int hi_rank = o > rank ? o : rank;
-      const int64_t b0 = (int64_t)hi_rank * per / 128, b1 = b0 + (dist_ncols(n, hi_rank, per) + 127) / 128;
-      const int64_t mid = b0 + (b1 - b0 + 1) / 2;
-      if (o > rank) {  // rows: the lower half of o's blocks; columns: all of mine
-        rg.r0 = (int64_t)o * per;
-        rg.r1 = mid * 128 < n ? mid * 128 : n;
-        rg.c0 = col0;
-        rg.c1 = col0 + ncols;
-      } else {  // rows: all of o's; columns: the upper half of my blocks
-        rg.r0 = (int64_t)o * per;
-        rg.r1 = rg.r0 + o_rows;
-        rg.c0 = mid * 128;
-        rg.c1 = col0 + ncols;
-      }
-      if (rg.r1 <= rg.r0 || rg.c1 <= rg.c0) rg = DistRegion();
-    }
+    for (int o = 0; o < world; ++o) plan.region[o] = dist_region(n, world, rank, per, o, staged);
     B200W_CUDA(cudaMalloc(&plan.d_list, (plan.list.size() + 1) * sizeof(int2)));
     B200W_CUDA(cudaMalloc(&plan.d_cstart, cstart.size() * sizeof(int)));
     B200W_CUDA(cudaMalloc(&plan.d_row_off, row_off.size() * sizeof(int)));

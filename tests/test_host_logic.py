@@ -254,3 +254,52 @@ def test_sharded_symmetric_sweep_schedule_covers_every_block_pair_once(n, world)
     if len(busy) > 1:
         assert max(busy) - min(busy) <= 0.1 * max(busy) + 4
     assert lib.b200w_sweep_dist_tiles(n, 1, 0, per, None, 0) == -1
+
+
+@pytest.mark.parametrize("n,world", [(2304, 2), (2500, 4), (600, 2), (200, 4), (5000, 8), (3001, 3), (50000, 4), (1000, 8)])
+def test_sharded_symmetric_sweep_delivers_every_cell_of_every_block_once(n, world):
+    """Data flow of b200w_dev_sweep_dist on the host: who writes which 64 x 64 cell of which rank's similarity block.
+    A tile (rows = block a, columns = 64-column tile c of the computing rank) is stored transposed into the computing
+    rank's own rows and in the direct orientation to the owner of a -- into its block (own rows, or a peer's over NVLink
+    with two ranks) or, with more ranks, into the staging rectangle that the copy engines push.  Every cell of every
+    rank's block must be written exactly once, and a rectangle must hold exactly the tiles computed for that peer."""
+    from pywgcna_b200 import _lib as L
+    from pywgcna_b200.device import ALIGN, rows_per_rank
+
+    lib = L.load()
+    per = rows_per_rank(n, world, ALIGN)
+    n64 = -(-n // 64)
+    written = np.zeros((n64, n64), dtype=np.int32)  # global (row tile, column tile) of the n x n similarity
+    staged = None
+    for rank in range(world):
+        cnt = lib.b200w_sweep_dist_tiles(n, world, rank, per, None, 0)
+        xy = np.zeros((max(cnt, 1), 2), dtype=np.int32)
+        lib.b200w_sweep_dist_tiles(n, world, rank, per, xy.ctypes.data, cnt)
+        reg = np.zeros((world, 4), dtype=np.int64)
+        mode = lib.b200w_sweep_dist_regions(n, world, rank, per, reg.ctypes.data)
+        assert mode in (0, 1) and (staged is None or staged == mode)
+        staged = mode
+        assert mode == (1 if world > 2 else 0)
+        owed = {o: set() for o in range(world)}
+        for a, jt in xy[:cnt]:
+            a, c = int(a), (rank * per) // 64 + int(jt)
+            rows_a = [t for t in (2 * a, 2 * a + 1) if t * 64 < n]
+            for t in rows_a:  # transposed: rows = the column tile's genes, columns = block a
+                written[c, t] += 1
+            if a != c // 2:  # off the diagonal block: the direct orientation goes to the owner of a
+                owner = (a * 128) // per
+                for t in rows_a:
+                    written[t, c] += 1
+                    if owner != rank:
+                        owed[owner].add((t, c))
+        for o in range(world):
+            r0, r1, c0, c1 = (int(v) for v in reg[o])
+            if not mode or o == rank:
+                assert (r0, r1, c0, c1) == (0, 0, 0, 0)
+                continue
+            cells = {(t, c) for t in range(r0 // 64, -(-r1 // 64)) for c in range(c0 // 64, -(-c1 // 64))}
+            assert cells == owed[o], (rank, o, len(cells), len(owed[o]))
+            if cells:  # inside o's rows and this rank's columns, starting on tile boundaries
+                assert r0 == o * per and r1 <= min(n, (o + 1) * per) and r0 % 128 == 0 and c0 % 128 == 0
+                assert rank * per <= c0 and c1 == min(n, (rank + 1) * per)
+    assert written.min() == 1 and written.max() == 1
